@@ -1,0 +1,231 @@
+"""Known-answer tests that pin the oracle (KAT-1 .. KAT-8).
+
+The upstream repository ships no tests or golden vectors, so these closed-form cases and
+the library cross-checks are what the oracle is anchored to.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import photometric as O
+from coivo_b200.synthetic import make_intrinsics, make_triplets, make_sequence
+
+
+def _eye_pose(B, N):
+    return torch.eye(4).reshape(1, 1, 4, 4).repeat(B, N, 1, 1)
+
+
+def test_kat1_identity_pose_reproduces_source_exactly():
+    d = make_triplets(2, 24, 40, seed=3)
+    K = d["K"]
+    Dhat = d["depth"][0]
+    u, v, valid, _ = O.reproject(Dhat, K, _eye_pose(2, 1)[:, 0])
+    uu = torch.arange(40.0).reshape(1, 1, 40).expand(2, 24, 40)
+    vv = torch.arange(24.0).reshape(1, 24, 1).expand(2, 24, 40)
+    # u' = (fx*X + cx*Z)/Z is exact up to a few ulp; the sampled image must still equal the source
+    assert torch.allclose(u, uu, atol=2e-5) and torch.allclose(v, vv, atol=2e-5)
+    Iw = O.bilinear_sample(d["srcs"][:, 0], uu, vv)
+    assert torch.equal(Iw, d["srcs"][:, 0])
+    assert valid[:, 1:-1, 1:-1].all()
+
+
+def test_kat2_lcc_recovers_gain_and_bias():
+    d = make_triplets(2, 32, 48, seed=1)
+    tgt = d["tgt"]
+    alpha_, beta_ = 1.25, -0.04
+    src = (tgt - beta_) / alpha_
+    valid = torch.ones(2, 32, 48, dtype=torch.bool)
+    a, b = O.lcc_fit(src, tgt, valid)
+    assert torch.allclose(a, torch.full_like(a, alpha_), atol=2e-4)
+    assert torch.allclose(b, torch.full_like(b, beta_), atol=2e-4)
+    pe = O.photometric_error(a.reshape(2, 1, 1, 1) * src + b.reshape(2, 1, 1, 1), tgt)
+    assert pe.max() < 1e-4
+
+
+def test_kat3_fronto_parallel_integer_shift():
+    B, H, W = 1, 16, 40
+    K = make_intrinsics(B, H, W)
+    fx = K[0, 0, 0].item()
+    d0 = 2.0
+    s = 3
+    T = torch.eye(4).reshape(1, 4, 4).clone()
+    T[0, 0, 3] = s * d0 / fx
+    D = torch.full((B, 1, H, W), d0)
+    u, v, valid, _ = O.reproject(D, K, T)
+    uu = torch.arange(W, dtype=torch.float32).reshape(1, 1, W).expand(B, H, W)
+    assert torch.allclose(u, uu + s, atol=1e-4)
+    g = torch.Generator().manual_seed(0)
+    src = torch.rand(B, 3, H, W, generator=g)
+    Iw = O.bilinear_sample(src, torch.round(u), torch.round(v))
+    assert torch.equal(Iw[..., : W - s], src[..., s:])
+    # columns whose sample falls beyond W-1 are invalid
+    exp_valid = (uu + s) <= W - 1
+    got = valid.clone()
+    # tolerate the exact-boundary column only
+    assert torch.equal(got[..., : W - s - 1], exp_valid[..., : W - s - 1])
+    assert not got[..., W - s + 1:].any()
+
+
+def test_kat4_constant_images():
+    B, H, W = 1, 12, 20
+    x = torch.full((B, 3, H, W), 0.6)
+    y = torch.full((B, 3, H, W), 0.4)
+    pe = O.photometric_error(x, y)
+    # sigma == 0 -> SSIM = (2*mx*my + C1)/(mx^2 + my^2 + C1)
+    ssim = (2 * 0.6 * 0.4 + O.SSIM_C1) / (0.36 + 0.16 + O.SSIM_C1)
+    expect = 0.85 * (1 - ssim) / 2 + 0.15 * 0.2
+    # fp32 cancellation in E[x^2]-mu^2 (~3e-8) against C2 = 9e-4 bounds the accuracy here
+    assert torch.allclose(pe, torch.full_like(pe, expect), atol=5e-5)
+    assert torch.allclose(O.photometric_error(x, x), torch.zeros(B, H, W), atol=5e-5)
+    a, b = O.lcc_fit(x, y, torch.ones(B, H, W, dtype=torch.bool))
+    assert abs(a.item()) < 1e-3 and abs(b.item() - 0.4) < 1e-3
+    a, b = O.lcc_fit(x, y, torch.zeros(B, H, W, dtype=torch.bool))
+    assert a.item() == 1.0 and b.item() == 0.0
+
+
+def test_kat5_points_behind_camera_invalid():
+    B, H, W = 1, 8, 12
+    K = make_intrinsics(B, H, W)
+    T = torch.eye(4).reshape(1, 4, 4).clone()
+    T[0, 2, 3] = -5.0                       # Z' = D - 5 < z_min
+    D = torch.full((B, 1, H, W), 1.5)
+    _, _, valid, Zp = O.reproject(D, K, T)
+    assert (Zp < O.Z_MIN).all() and not valid.any()
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_kat6_bilinear_matches_grid_sample_forward_and_backward(seed):
+    g = torch.Generator().manual_seed(seed)
+    B, C, H, W = 2, 3, 11, 17
+    src = torch.rand(B, C, H, W, generator=g, dtype=torch.float64).requires_grad_()
+    u = (torch.rand(B, H, W, generator=g, dtype=torch.float64) * (W + 3) - 2).requires_grad_()
+    v = (torch.rand(B, H, W, generator=g, dtype=torch.float64) * (H + 3) - 2).requires_grad_()
+    with torch.no_grad():
+        u[:, 0, 0] = 0.0
+        u[:, 0, 1] = W - 1.0                # exactly on the border: coordinate gradient must be 0
+        v[:, 1, 0] = 0.0
+        v[:, 1, 1] = H - 1.0
+    w = torch.rand(B, C, H, W, generator=g, dtype=torch.float64)
+    out = O.bilinear_sample(src, u, v)
+    gs, gu, gv = torch.autograd.grad((out * w).sum(), [src, u, v])
+    gx = 2 * u / (W - 1) - 1
+    gy = 2 * v / (H - 1) - 1
+    ref = F.grid_sample(src, torch.stack([gx, gy], -1), mode="bilinear", padding_mode="border", align_corners=True)
+    rs, ru, rv = torch.autograd.grad((ref * w).sum(), [src, u, v])
+    assert torch.allclose(out, ref, atol=1e-12)
+    assert torch.allclose(gs, rs, atol=1e-12)
+    assert torch.allclose(gu, ru, atol=1e-10) and torch.allclose(gv, rv, atol=1e-10)
+    assert gu[:, 0, 0].abs().max() == 0 and gu[:, 0, 1].abs().max() == 0
+
+
+def test_kat7_box_mean_matches_manual_reflect_sum():
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(2, 3, 9, 13, generator=g)
+    H, W = 9, 13
+    ref = torch.zeros_like(x)
+
+    def refl(i, n):
+        return -i if i < 0 else (2 * n - 2 - i if i >= n else i)
+
+    for dy in (-1, 0, 1):
+        for dx in (-1, 0, 1):
+            ys = torch.tensor([refl(i + dy, H) for i in range(H)])
+            xs = torch.tensor([refl(j + dx, W) for j in range(W)])
+            ref += x[:, :, ys][:, :, :, xs]
+    ref /= 9
+    assert torch.allclose(O.box3_reflect(x), ref, atol=1e-6)
+
+
+def test_kat8_smoothness_closed_forms():
+    B, h, w = 2, 10, 14
+    I = torch.full((B, 3, h, w), 0.3)
+    assert O.smoothness(torch.full((B, 1, h, w), 1.7), I).item() == 0.0
+    # inverse depth a linear ramp in x on a constant image: |d*_x - d*_{x+1}| = step / (mean + eps)
+    d = 1.0 + 0.1 * torch.arange(w, dtype=torch.float32).reshape(1, 1, 1, w).expand(B, 1, h, w)
+    D = 1.0 / d
+    expect = 0.1 / (d.mean().item() + 1e-7)
+    assert abs(O.smoothness(D, I).item() - expect) < 1e-5
+    # an image edge damps the term by exp(-|dI|)
+    I2 = I.clone()
+    I2[..., w // 2:] += 0.5
+    got = O.smoothness(D, I2).item()
+    exp2 = expect * ((w - 2) + math.exp(-0.5)) / (w - 1)
+    assert abs(got - exp2) < 1e-5
+
+
+def test_upsample_matches_interpolate():
+    g = torch.Generator().manual_seed(0)
+    for (H, W, k) in [(32, 48, 1), (32, 48, 3), (27, 45, 2)]:
+        h, w = H >> k, W >> k
+        D = torch.rand(2, 1, h, w, generator=g) + 1
+        ref = F.interpolate(D, size=(H, W), mode="bilinear", align_corners=False)
+        assert torch.allclose(O.upsample_depth(D, H, W), ref, atol=1e-5)
+    D = torch.rand(1, 1, 8, 8)
+    assert O.upsample_depth(D, 8, 8) is D
+
+
+def test_loss_properties_and_shard_additivity():
+    d = make_triplets(4, 32, 48, seed=5)
+    args = (d["depth"], d["pose"], d["K"], d["tgt"], d["srcs"])
+    loss, valid, sel, ab = O.photometric_loss(*args, return_masks=True)
+    assert loss.item() >= 0
+    assert valid.shape == (4, 2, 4, 32, 48) and sel.shape == (4, 4, 32, 48) and ab.shape == (4, 2, 4, 2)
+    assert valid.dtype == torch.uint8 and sel.dtype == torch.uint8 and sel.max() <= 3
+    parts = []
+    for s in range(2):
+        sl = slice(2 * s, 2 * s + 2)
+        parts.append(O.photometric_loss([x[sl] for x in d["depth"]], d["pose"][sl], d["K"][sl], d["tgt"][sl], d["srcs"][sl]))
+    assert abs(loss.item() - 0.5 * (parts[0] + parts[1]).item()) < 1e-6
+    # sel_override with the oracle's own sel reproduces the loss
+    l2 = O.photometric_loss(*args, sel_override=sel, ab_override=ab)
+    assert abs(l2.item() - loss.item()) < 1e-7
+
+
+def test_swapping_identical_sources_changes_only_sel():
+    d = make_triplets(1, 24, 32, seed=2)
+    srcs = d["srcs"].clone()
+    srcs[:, 1] = srcs[:, 0]
+    pose = d["pose"].clone()
+    pose[:, 1] = pose[:, 0]
+    l1, _, sel, _ = O.photometric_loss(d["depth"], pose, d["K"], d["tgt"], srcs, return_masks=True)
+    assert not (sel == 1).any() and not (sel == 3).any()      # first index wins every tie
+    assert l1.item() >= 0
+
+
+def test_lcc_flags():
+    d = make_triplets(1, 24, 32, seed=7)
+    args = (d["depth"], d["pose"], d["K"], d["tgt"], d["srcs"])
+    l_on = O.photometric_loss(*args)
+    l_off, _, _, ab = O.photometric_loss(*args, lcc=False, return_masks=True)
+    assert abs(l_off.item() - l_on.item()) > 1e-4    # calibration changes the loss
+    assert torch.equal(ab[..., 0], torch.ones_like(ab[..., 0])) and ab[..., 1].abs().max() == 0
+    srcs = d["srcs"].clone().requires_grad_()
+    ga = torch.autograd.grad(O.photometric_loss(d["depth"], d["pose"], d["K"], d["tgt"], srcs), srcs)[0]
+    gd = torch.autograd.grad(O.photometric_loss(d["depth"], d["pose"], d["K"], d["tgt"], srcs, lcc_detach=True), srcs)[0]
+    assert not torch.allclose(ga, gd)
+
+
+def test_validation_errors():
+    d = make_triplets(1, 16, 24, seed=0)
+    with pytest.raises(ValueError):
+        O.photometric_loss(d["depth"][::-1], d["pose"], d["K"], d["tgt"], d["srcs"])
+    with pytest.raises(ValueError):
+        O.photometric_loss(d["depth"], d["pose"][:, :1], d["K"], d["tgt"], d["srcs"])
+
+
+def test_consistency_sweep_shapes_and_identity():
+    s = make_sequence(6, 24, 32, seed=0)
+    out = O.consistency(s["depth"], s["pose"], s["K"], s["frames"])
+    assert out.shape == (5, 4)
+    assert (out[:, 3] > 0.5).all() and (out[:, 3] <= 1).all() and (out[:, 0] >= 0).all()
+    # a static scene with identity motion and a pure gain change: LCC undoes it, pe ~ 0
+    fr = s["frames"][:1].repeat(3, 1, 1, 1)
+    fr[1] = fr[1] * 0.8 + 0.05
+    fr[2] = fr[1]
+    eye = torch.eye(4).repeat(2, 1, 1)
+    out = O.consistency(s["depth"][:3], eye, s["K"], fr)
+    assert abs(out[0, 1].item() - 1.25) < 1e-3 and abs(out[0, 2].item() + 0.0625) < 1e-3
+    assert out[0, 0].item() < 1e-4 and out[1, 0].item() < 1e-4
+    assert out[0, 3].item() > 0.9          # border rows/columns may round just outside
