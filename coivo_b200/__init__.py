@@ -1,0 +1,11 @@
+"""coivo_b200 -- B200-native photometric-loss hot path of ColVO (HNUicda/CoIVO).
+
+Only the path BASELINE.json's north_star names lives here: the fused CUDA kernels and their
+C ABI (`csrc/`, `include/colvo.h`) and the host-side operator that mirrors the interface a
+PyTorch training loop calls (`photometric_loss`, `consistency`).  CUDA-only by design.
+"""
+from .loss import photometric_loss, HostStepper  # noqa: F401
+from .consistency import consistency  # noqa: F401
+from . import dist, synthetic  # noqa: F401
+
+__all__ = ["photometric_loss", "consistency", "HostStepper", "dist", "synthetic"]

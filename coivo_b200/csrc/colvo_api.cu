@@ -1,0 +1,330 @@
+// C ABI of libcolvo_b200.so (include/colvo.h).  Host-side only: descriptor validation,
+// workspace carving and kernel launches on the caller's stream.  No allocation, no
+// synchronisation, no retained state; there is no CPU fallback.
+#include <cuda_runtime.h>
+#include <string.h>
+
+#include "../../include/colvo.h"
+#include "colvo_kernels.cuh"
+
+using namespace colvo;
+
+namespace {
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+inline int div_up(int a, int b) { return (a + b - 1) / b; }
+
+struct Carver {
+  char* base;
+  size_t off;
+  explicit Carver(void* p) : base(static_cast<char*>(p)), off(0) {}
+  template <typename T>
+  T* take(size_t count) {
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off = align_up(off + count * sizeof(T));
+    return p;
+  }
+};
+
+int check_desc(const ColvoDesc* d) {
+  if (!d) return COLVO_E_NULL_PTR;
+  if (d->B < 1 || d->N < 1 || d->N > COLVO_MAX_SOURCES || d->S < 1 || d->S > COLVO_MAX_SCALES) return COLVO_E_BAD_DESC;
+  if (d->H < 2 || d->W < 2) return COLVO_E_BAD_DESC;
+  if ((long long)d->H * d->W > (1ll << 28)) return COLVO_E_BAD_DESC;
+  if (d->B > 65535) return COLVO_E_BAD_DESC;
+  for (int k = 0; k < d->S; ++k) {
+    if (d->h[k] != (d->H >> k) || d->w[k] != (d->W >> k)) return COLVO_E_BAD_DESC;
+    if (d->h[k] < 1 || d->w[k] < 1) return COLVO_E_BAD_DESC;
+  }
+  return 0;
+}
+
+void fill_params(KP& P, const ColvoDesc* d) {
+  memset(&P, 0, sizeof(P));
+  P.B = d->B; P.N = d->N; P.S = d->S; P.H = d->H; P.W = d->W; P.HW = d->H * d->W;
+  for (int k = 0; k < d->S; ++k) {
+    P.h[k] = d->h[k];
+    P.w[k] = d->w[k];
+    P.ry[k] = (float)((double)d->h[k] / (double)d->H);
+    P.rx[k] = (float)((double)d->w[k] / (double)d->W);
+    P.depth_bs[k] = (long long)d->h[k] * d->w[k];
+  }
+  P.alpha = d->alpha; P.c1 = d->c1; P.c2 = d->c2; P.eps_proj = d->eps_proj; P.eps_lcc = d->eps_lcc;
+  P.eps_disp = d->eps_disp; P.z_min = d->z_min; P.smooth_weight = d->smooth_weight;
+  P.flags = d->flags;
+  P.tgt_bs = 3ll * P.HW;
+  P.src_ns = 3ll * P.HW;
+  P.src_bs = (long long)d->N * 3ll * P.HW;
+  P.K_bs = 9; P.T_ns = 16; P.T_bs = 16 * d->N;
+  P.tiles_x = div_up(d->W, kTileW);
+  P.tiles_y = div_up(d->H, kTileH);
+}
+
+int stat_chunks(const ColvoDesc* d) { return div_up(d->H * d->W, kThreads * kStatPPT); }
+
+size_t carve_fwd(const ColvoDesc* d, void* ws, FwdBuffers& F) {
+  Carver c(ws);
+  const size_t BNS = (size_t)d->B * d->N * d->S, BS = (size_t)d->B * d->S;
+  const size_t tiles = (size_t)div_up(d->W, kTileW) * div_up(d->H, kTileH);
+  F.stat_chunks = stat_chunks(d);
+  F.stat_part = c.take<double>(BNS * F.stat_chunks * 5);
+  F.disp_part = c.take<double>(BS * kSmoothChunks);
+  F.smooth_part = c.take<double>(BS * kSmoothChunks * 2);
+  F.loss_part = c.take<float>((size_t)d->B * tiles);
+  F.g_part = c.take<float>((size_t)d->B * tiles * d->N * kMaxS * 2);
+  F.pyr[0] = nullptr;
+  for (int k = 1; k < kMaxS; ++k) F.pyr[k] = (k < d->S) ? c.take<float>((size_t)d->B * 3 * d->h[k] * d->w[k]) : nullptr;
+  return c.off;
+}
+
+size_t carve_bwd(const ColvoDesc* d, void* ws, BwdBuffers& Bw) {
+  Carver c(ws);
+  const size_t BS = (size_t)d->B * d->S;
+  const size_t tiles = (size_t)div_up(d->W, kTileW) * div_up(d->H, kTileH);
+  const size_t HW = (size_t)d->H * d->W;
+  Bw.pyr[0] = nullptr;
+  Bw.dDhat[0] = nullptr;
+  for (int k = 1; k < kMaxS; ++k) Bw.pyr[k] = (k < d->S) ? c.take<float>((size_t)d->B * 3 * d->h[k] * d->w[k]) : nullptr;
+  for (int k = 1; k < kMaxS; ++k) Bw.dDhat[k] = (k < d->S) ? c.take<float>((size_t)d->B * HW) : nullptr;
+  Bw.pose_part = c.take<float>((size_t)d->B * tiles * d->N * 12);
+  for (int k = 0; k < kMaxS; ++k) Bw.s_field[k] = (k < d->S) ? c.take<float>((size_t)d->B * d->h[k] * d->w[k]) : nullptr;
+  Bw.sd_part = c.take<double>(BS * kSmoothChunks);
+  return c.off;
+}
+
+__global__ void k_fill_one(float* p) { *p = 1.0f; }
+
+}  // namespace
+
+extern "C" {
+
+int colvo_version(void) { return COLVO_VERSION; }
+
+const char* colvo_error_string(int rc) {
+  switch (rc) {
+    case 0: return "success";
+    case COLVO_E_BAD_DESC: return "colvo: bad descriptor (sizes, pyramid shapes h_k = H >> k, 1 <= N <= 2, 1 <= S <= 4)";
+    case COLVO_E_WORKSPACE: return "colvo: workspace too small (see colvo_workspace_bytes)";
+    case COLVO_E_NULL_PTR: return "colvo: required pointer is NULL";
+    case COLVO_E_MISALIGNED: return "colvo: pointer not aligned (fp32 buffers 4 B, saved 8 B, workspace 256 B)";
+    case COLVO_E_UNSUPPORTED: return "colvo: unsupported configuration";
+    default: break;
+  }
+  if (rc > 0) return cudaGetErrorString(static_cast<cudaError_t>(rc));
+  return "colvo: unknown error code";
+}
+
+int colvo_desc_init(ColvoDesc* d, int32_t B, int32_t N, int32_t S, int32_t H, int32_t W, uint32_t flags) {
+  if (!d) return COLVO_E_NULL_PTR;
+  memset(d, 0, sizeof(*d));
+  d->B = B; d->N = N; d->S = S; d->H = H; d->W = W;
+  for (int k = 0; k < COLVO_MAX_SCALES && k < S; ++k) { d->h[k] = H >> k; d->w[k] = W >> k; }
+  d->alpha = 0.85f; d->c1 = 1e-4f; d->c2 = 9e-4f; d->eps_proj = 1e-7f; d->eps_lcc = 1e-6f; d->eps_disp = 1e-7f;
+  d->z_min = 1e-3f; d->smooth_weight = 1e-3f;
+  d->flags = flags;
+  return check_desc(d);
+}
+
+int colvo_workspace_bytes(const ColvoDesc* d, size_t* bytes) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  if (!bytes) return COLVO_E_NULL_PTR;
+  FwdBuffers F;
+  BwdBuffers Bw;
+  size_t a = carve_fwd(d, nullptr, F), b = carve_bwd(d, nullptr, Bw);
+  *bytes = a > b ? a : b;
+  return 0;
+}
+
+int colvo_saved_doubles(const ColvoDesc* d, size_t* count) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  if (!count) return COLVO_E_NULL_PTR;
+  *count = (size_t)d->B * d->N * d->S * kSavedPerFrame + (size_t)d->B * d->S;
+  return 0;
+}
+
+int colvo_photo_forward(const ColvoDesc* d, const float* tgt, const float* srcs, const float* const* depth,
+                        const float* K, const float* T, float* loss, float* ab, uint8_t* valid, uint8_t* sel,
+                        double* saved, void* ws, size_t ws_bytes, void* stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  if (!tgt || !srcs || !depth || !K || !T || !loss || !ab || !ws) return COLVO_E_NULL_PTR;
+  for (int k = 0; k < d->S; ++k)
+    if (!depth[k]) return COLVO_E_NULL_PTR;
+  if ((d->flags & COLVO_F_SAVE_FOR_BWD) && (!sel || !saved)) return COLVO_E_NULL_PTR;
+  if (((uintptr_t)ws & 255u) || ((uintptr_t)saved & 7u)) return COLVO_E_MISALIGNED;
+  FwdBuffers F;
+  if (carve_fwd(d, ws, F) > ws_bytes) return COLVO_E_WORKSPACE;
+  KP P;
+  fill_params(P, d);
+  P.tgt = tgt; P.srcs = srcs; P.K = K; P.T = T;
+  for (int k = 0; k < d->S; ++k) P.depth[k] = depth[k];
+  return (int)launch_forward(P, F, loss, ab, valid, sel, saved, static_cast<cudaStream_t>(stream));
+}
+
+int colvo_photo_backward(const ColvoDesc* d, const float* tgt, const float* srcs, const float* const* depth,
+                         const float* K, const float* T, const float* grad_loss, const uint8_t* sel,
+                         const double* saved, float* const* grad_depth, float* grad_T, float* grad_srcs, void* ws,
+                         size_t ws_bytes, void* stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  if (!tgt || !srcs || !depth || !K || !T || !grad_loss || !sel || !saved || !grad_depth || !grad_T || !ws)
+    return COLVO_E_NULL_PTR;
+  for (int k = 0; k < d->S; ++k)
+    if (!depth[k] || !grad_depth[k]) return COLVO_E_NULL_PTR;
+  const bool want_src = !(d->flags & COLVO_F_NO_SRC_GRAD);
+  if (want_src && !grad_srcs) return COLVO_E_NULL_PTR;
+  if (((uintptr_t)ws & 255u) || ((uintptr_t)saved & 7u)) return COLVO_E_MISALIGNED;
+  BwdBuffers Bw;
+  if (carve_bwd(d, ws, Bw) > ws_bytes) return COLVO_E_WORKSPACE;
+  KP P;
+  fill_params(P, d);
+  P.tgt = tgt; P.srcs = srcs; P.K = K; P.T = T;
+  for (int k = 0; k < d->S; ++k) P.depth[k] = depth[k];
+  return (int)launch_backward(P, Bw, grad_loss, sel, saved, grad_depth, grad_T, want_src ? grad_srcs : nullptr,
+                              static_cast<cudaStream_t>(stream));
+}
+
+// ---- consistency sweep ----------------------------------------------------------------------
+static size_t carve_consistency(int F, int H, int W, void* ws, double** stat, int* chunks, double** pe_part,
+                                float** ab) {
+  Carver c(ws);
+  const size_t Pn = (size_t)(F - 1);
+  const size_t tiles = (size_t)div_up(W, kTileW) * div_up(H, kTileH);
+  *chunks = div_up(H * W, kThreads * kStatPPT);
+  *stat = c.take<double>(Pn * (*chunks) * 5);
+  *pe_part = c.take<double>(Pn * tiles * 2);
+  *ab = c.take<float>(Pn * 2);
+  return c.off;
+}
+
+int colvo_consistency_workspace_bytes(int32_t F, int32_t H, int32_t W, size_t* bytes) {
+  if (!bytes) return COLVO_E_NULL_PTR;
+  if (F < 2 || H < 2 || W < 2 || F - 1 > 65535) return COLVO_E_BAD_DESC;
+  double *a, *b;
+  float* c;
+  int ch;
+  *bytes = carve_consistency(F, H, W, nullptr, &a, &ch, &b, &c);
+  return 0;
+}
+
+int colvo_consistency(int32_t F, int32_t H, int32_t W, uint32_t flags, const float* frames, const float* depth,
+                      const float* T, const float* K, int32_t k_per_pair, float* out, void* ws, size_t ws_bytes,
+                      void* stream) {
+  if (F < 2 || H < 2 || W < 2 || F - 1 > 65535) return COLVO_E_BAD_DESC;
+  if (!frames || !depth || !T || !K || !out || !ws) return COLVO_E_NULL_PTR;
+  if ((uintptr_t)ws & 255u) return COLVO_E_MISALIGNED;
+  double *stat, *pe_part;
+  float* ab;
+  int chunks;
+  if (carve_consistency(F, H, W, ws, &stat, &chunks, &pe_part, &ab) > ws_bytes) return COLVO_E_WORKSPACE;
+  ColvoDesc d;
+  int rc = colvo_desc_init(&d, F - 1, 1, 1, H, W, flags & COLVO_F_LCC);
+  if (rc) return rc;
+  KP P;
+  fill_params(P, &d);
+  // pair i: target = frames[i], source = frames[i+1]: one array, two views
+  P.tgt = frames;
+  P.srcs = frames + 3ll * P.HW;
+  P.tgt_bs = 3ll * P.HW;
+  P.src_bs = 3ll * P.HW;
+  P.src_ns = 0;
+  P.depth[0] = depth;
+  P.K = K;
+  P.K_bs = k_per_pair ? 9 : 0;
+  P.T = T;
+  P.T_bs = 16;
+  P.T_ns = 0;
+  return (int)launch_consistency(P, stat, chunks, pe_part, ab, out, static_cast<cudaStream_t>(stream));
+}
+
+// ---- end-to-end step on host buffers ----------------------------------------------------------
+struct Arena {
+  float *tgt, *srcs, *depth[kMaxS], *K, *T, *loss, *ab, *one, *grad_depth[kMaxS], *grad_T, *grad_srcs;
+  uint8_t* sel;
+  double* saved;
+  void* ws;
+  size_t ws_bytes;
+};
+
+static size_t carve_arena(const ColvoDesc* d, void* base, Arena& A) {
+  Carver c(base);
+  const size_t HW = (size_t)d->H * d->W, B = d->B, N = d->N, S = d->S;
+  A.tgt = c.take<float>(B * 3 * HW);
+  A.srcs = c.take<float>(B * N * 3 * HW);
+  for (int k = 0; k < kMaxS; ++k) A.depth[k] = (k < d->S) ? c.take<float>(B * d->h[k] * d->w[k]) : nullptr;
+  A.K = c.take<float>(B * 9);
+  A.T = c.take<float>(B * N * 16);
+  A.loss = c.take<float>(1);
+  A.ab = c.take<float>(B * N * S * 2);
+  A.one = c.take<float>(1);
+  for (int k = 0; k < kMaxS; ++k) A.grad_depth[k] = (k < d->S) ? c.take<float>(B * d->h[k] * d->w[k]) : nullptr;
+  A.grad_T = c.take<float>(B * N * 16);
+  A.grad_srcs = c.take<float>(B * N * 3 * HW);
+  A.sel = c.take<uint8_t>(B * S * HW);
+  size_t ns = 0;
+  colvo_saved_doubles(d, &ns);
+  A.saved = c.take<double>(ns);
+  colvo_workspace_bytes(d, &A.ws_bytes);
+  A.ws = c.take<char>(A.ws_bytes);
+  return c.off;
+}
+
+int colvo_step_host_arena_bytes(const ColvoDesc* d, size_t* bytes) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  if (!bytes) return COLVO_E_NULL_PTR;
+  Arena A;
+  *bytes = carve_arena(d, nullptr, A);
+  return 0;
+}
+
+int colvo_photo_step_host(const ColvoDesc* d_in, const float* h_tgt, const float* h_srcs, const float* const* h_depth,
+                          const float* h_K, const float* h_T, float* h_loss, float* const* h_grad_depth,
+                          float* h_grad_T, float* h_grad_srcs, void* arena, size_t arena_bytes, void* stream) {
+  int rc = check_desc(d_in);
+  if (rc) return rc;
+  if (!h_tgt || !h_srcs || !h_depth || !h_K || !h_T || !h_loss || !h_grad_depth || !h_grad_T || !arena)
+    return COLVO_E_NULL_PTR;
+  ColvoDesc d = *d_in;
+  d.flags |= COLVO_F_SAVE_FOR_BWD;
+  const bool want_src = !(d.flags & COLVO_F_NO_SRC_GRAD);
+  if (want_src && !h_grad_srcs) return COLVO_E_NULL_PTR;
+  if ((uintptr_t)arena & 255u) return COLVO_E_MISALIGNED;
+  Arena A;
+  if (carve_arena(&d, arena, A) > arena_bytes) return COLVO_E_WORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t HW = (size_t)d.H * d.W, B = d.B, N = d.N;
+  cudaError_t e;
+#define CV_COPY(dst, src, count, kind)                                                      \
+  do {                                                                                      \
+    e = cudaMemcpyAsync((dst), (src), sizeof(float) * (count), (kind), st);                 \
+    if (e != cudaSuccess) return (int)e;                                                    \
+  } while (0)
+  CV_COPY(A.tgt, h_tgt, B * 3 * HW, cudaMemcpyHostToDevice);
+  CV_COPY(A.srcs, h_srcs, B * N * 3 * HW, cudaMemcpyHostToDevice);
+  for (int k = 0; k < d.S; ++k) {
+    if (!h_depth[k] || !h_grad_depth[k]) return COLVO_E_NULL_PTR;
+    CV_COPY(A.depth[k], h_depth[k], B * d.h[k] * d.w[k], cudaMemcpyHostToDevice);
+  }
+  CV_COPY(A.K, h_K, B * 9, cudaMemcpyHostToDevice);
+  CV_COPY(A.T, h_T, B * N * 16, cudaMemcpyHostToDevice);
+  k_fill_one<<<1, 1, 0, st>>>(A.one);
+  const float* depth_p[kMaxS] = {A.depth[0], A.depth[1], A.depth[2], A.depth[3]};
+  float* gdepth_p[kMaxS] = {A.grad_depth[0], A.grad_depth[1], A.grad_depth[2], A.grad_depth[3]};
+  rc = colvo_photo_forward(&d, A.tgt, A.srcs, depth_p, A.K, A.T, A.loss, A.ab, nullptr, A.sel, A.saved, A.ws,
+                           A.ws_bytes, stream);
+  if (rc) return rc;
+  rc = colvo_photo_backward(&d, A.tgt, A.srcs, depth_p, A.K, A.T, A.one, A.sel, A.saved, gdepth_p, A.grad_T,
+                            want_src ? A.grad_srcs : nullptr, A.ws, A.ws_bytes, stream);
+  if (rc) return rc;
+  CV_COPY(h_loss, A.loss, 1, cudaMemcpyDeviceToHost);
+  for (int k = 0; k < d.S; ++k) CV_COPY(h_grad_depth[k], A.grad_depth[k], B * d.h[k] * d.w[k], cudaMemcpyDeviceToHost);
+  CV_COPY(h_grad_T, A.grad_T, B * N * 16, cudaMemcpyDeviceToHost);
+  if (want_src) CV_COPY(h_grad_srcs, A.grad_srcs, B * N * 3 * HW, cudaMemcpyDeviceToHost);
+#undef CV_COPY
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,151 @@
+// Kernel parameter block, launch geometry and device helpers shared by the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "colvo_math.cuh"
+
+namespace colvo {
+
+constexpr int kMaxS = 4;
+constexpr int kMaxN = 2;
+constexpr int kThreads = 256;
+constexpr int kTileW = 32;     // one warp = one tile row: coalesced 128 B rows
+constexpr int kTileH = 8;
+constexpr int kStatPPT = 8;    // pixels per thread in the LCC statistics pass
+constexpr int kSmoothChunks = 16;
+
+// saved[] layout (doubles): per (b,n,k) kSavedPerFrame values, then per (b,k) the mean inverse depth
+constexpr int kSavedPerFrame = 8;   // n, mean_x, mean_y, 1/(n (var+eps)), a, b, G_a, G_b
+
+struct KP {
+  int B, N, S, H, W, HW;
+  int h[kMaxS], w[kMaxS];
+  float ry[kMaxS], rx[kMaxS];        // h_k / H, w_k / W rounded once to fp32 (oracle._upsample_axis)
+  float alpha, c1, c2, eps_proj, eps_lcc, eps_disp, z_min, smooth_weight;
+  unsigned flags;
+  const float* tgt;                  // [B,3,H,W]
+  const float* srcs;                 // [B,N,3,H,W]
+  const float* depth[kMaxS];         // [B,1,h_k,w_k]
+  const float* K;                    // [B,3,3]
+  const float* T;                    // [B,N,4,4]
+  long long tgt_bs, src_bs, src_ns;  // element strides (the consistency sweep aliases one frame array)
+  long long depth_bs[kMaxS];
+  int K_bs, T_bs, T_ns;
+  int tiles_x, tiles_y;
+};
+
+__device__ __forceinline__ Cam load_cam(const KP& P, int b) {
+  const float* k = P.K + (long long)b * P.K_bs;
+  Cam c;
+  c.fx = __ldg(k + 0);
+  c.fy = __ldg(k + 4);
+  c.cx = __ldg(k + 2);
+  c.cy = __ldg(k + 5);
+  return c;
+}
+__device__ __forceinline__ Pose load_pose(const KP& P, int b, int n) {
+  const float* t = P.T + (long long)b * P.T_bs + (long long)n * P.T_ns;
+  Pose p;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    p.r[3 * i + 0] = __ldg(t + 4 * i + 0);
+    p.r[3 * i + 1] = __ldg(t + 4 * i + 1);
+    p.r[3 * i + 2] = __ldg(t + 4 * i + 2);
+    p.t[i] = __ldg(t + 4 * i + 3);
+  }
+  return p;
+}
+
+// Row 0: up-sampled depth at a full-resolution pixel (identity at k == 0).
+__device__ __forceinline__ float depth_at(const KP& P, const float* __restrict__ Dk, int k, int px, int py) {
+  if (k == 0) return __ldg(Dk + py * P.W + px);
+  const int wk = P.w[k];
+  Axis ay = upsample_axis(py, P.ry[k], P.h[k]);
+  Axis ax = upsample_axis(px, P.rx[k], wk);
+  float d00 = __ldg(Dk + ay.i0 * wk + ax.i0);
+  float d01 = __ldg(Dk + ay.i0 * wk + ax.i1);
+  float d10 = __ldg(Dk + ay.i1 * wk + ax.i0);
+  float d11 = __ldg(Dk + ay.i1 * wk + ax.i1);
+  return upsample_blend(d00, d01, d10, d11, ax.w1, ay.w1);
+}
+
+// Rows 1-4 for one pixel: geometry, taps and the three raw warped channel values.
+struct Texels { float i00[3], i01[3], i10[3], i11[3]; };
+__device__ __forceinline__ void warp_pixel(const KP& P, const float* __restrict__ Dk, int k,
+                                           const float* __restrict__ src, const Cam& cam, const Pose& pose, int px,
+                                           int py, Geo& g, Taps& t, Texels& tx, float (&x)[3]) {
+  float D = depth_at(P, Dk, k, px, py);
+  g = reproject(px, py, D, cam, pose, P.W, P.H, P.eps_proj, P.z_min);
+  t = make_taps(g.u, g.v, P.W, P.H);
+  const int o00 = t.y0 * P.W + t.x0, o01 = t.y0 * P.W + t.x1;
+  const int o10 = t.y1 * P.W + t.x0, o11 = t.y1 * P.W + t.x1;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float* p = src + (long long)c * P.HW;
+    tx.i00[c] = __ldg(p + o00);
+    tx.i01[c] = __ldg(p + o01);
+    tx.i10[c] = __ldg(p + o10);
+    tx.i11[c] = __ldg(p + o11);
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) x[c] = bilerp(tx.i00[c], tx.i01[c], tx.i10[c], tx.i11[c], t.wx, t.wy);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Deterministic block reduction of NV per-thread values (kThreads threads); thread i < NV stores out[i].
+template <int NV, typename TV>
+__device__ __forceinline__ void block_reduce_store(TV (&v)[NV], TV* sm /* [kThreads/32][NV] */, TV* out) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    TV s = warp_sum(v[i]);
+    if (lane == 0) sm[wid * NV + i] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    TV s = 0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) s += sm[w * NV + threadIdx.x];
+    out[threadIdx.x] = s;
+  }
+}
+
+// ---- launchers implemented in colvo_fwd.cu / colvo_bwd.cu (called by colvo_api.cu) ----
+struct FwdBuffers {
+  double* stat_part;     // [B*N*S][stat_chunks][5]
+  int stat_chunks;
+  float* pyr[kMaxS];     // target pyramid, k >= 1: [B,3,h_k,w_k]
+  double* disp_part;     // [B*S][kSmoothChunks]
+  double* smooth_part;   // [B*S][kSmoothChunks][2]
+  float* loss_part;      // [B*tiles]
+  float* g_part;         // [B*tiles][N*S*2]
+};
+struct BwdBuffers {
+  float* pyr[kMaxS];     // target pyramid (rebuilt: the forward's scratch is not kept alive)
+  float* dDhat[kMaxS];   // k >= 1: [B,H,W] full-resolution depth adjoint before the up-sample adjoint
+  float* pose_part;      // [B*tiles][N*12]
+  float* s_field[kMaxS]; // smoothness adjoint dL/dd* per pixel, [B,h_k,w_k]
+  double* sd_part;       // [B*S][kSmoothChunks]
+};
+
+cudaError_t launch_tgt_pyramid(const KP& P, float* const* pyr, cudaStream_t st);
+cudaError_t launch_forward(const KP& P, const FwdBuffers& W, float* loss, float* ab, uint8_t* valid, uint8_t* sel,
+                           double* saved, cudaStream_t st);
+cudaError_t launch_backward(const KP& P, const BwdBuffers& W, const float* grad_loss, const uint8_t* sel,
+                            const double* saved, float* const* grad_depth, float* grad_T, float* grad_srcs,
+                            cudaStream_t st);
+cudaError_t launch_consistency(const KP& P, double* stat_part, int stat_chunks, double* pe_part, float* ab,
+                               float* out, cudaStream_t st);
+
+}  // namespace colvo

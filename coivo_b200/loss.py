@@ -1,0 +1,220 @@
+"""`photometric_loss(depth, pose, K, tgt, srcs)` -- the drop-in operator of the path.
+
+ColVO couples depth and pose through a view-synthesis loss ("loss function constraints ...
+alignment of geometric projections between consecutive frames", /root/reference/README.md:7)
+with the LCC brightness recalibration of the adjacent frames (README.md:5,7).  Upstream ships
+no code, so the operator interface is the one BASELINE.json's north_star prescribes and
+SURVEY.md section 8(b) spells out; `oracle/photometric.py` has the same signature and is the
+parity reference.
+
+A `torch.autograd.Function` over the C ABI in include/colvo.h: PyTorch only provides device
+memory, the current stream and autograd plumbing.  CUDA-only: CPU tensors are rejected.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+
+
+def _check_inputs(depth, pose, K, tgt, srcs):
+    if not isinstance(depth, (list, tuple)) or not 1 <= len(depth) <= _lib.MAX_SCALES:
+        raise ValueError(f"depth must be a sequence of 1..{_lib.MAX_SCALES} tensors [B,1,h_k,w_k]")
+    tensors = list(depth) + [pose, K, tgt, srcs]
+    for t in tensors:
+        if not isinstance(t, torch.Tensor):
+            raise TypeError("all inputs must be torch.Tensor")
+    if tgt.dim() != 4 or tgt.shape[1] != 3:
+        raise ValueError("tgt must be [B,3,H,W]")
+    B, _, H, W = tgt.shape
+    if srcs.dim() != 5 or srcs.shape[0] != B or tuple(srcs.shape[2:]) != (3, H, W):
+        raise ValueError("srcs must be [B,N,3,H,W]")
+    N = srcs.shape[1]
+    if not 1 <= N <= _lib.MAX_SOURCES:
+        raise ValueError(f"1 <= N <= {_lib.MAX_SOURCES} source frames are supported")
+    if tuple(pose.shape) != (B, N, 4, 4):
+        raise ValueError("pose must be [B,N,4,4]")
+    if tuple(K.shape) != (B, 3, 3):
+        raise ValueError("K must be [B,3,3]")
+    S = len(depth)
+    for k, d in enumerate(depth):
+        if tuple(d.shape) != (B, 1, H >> k, W >> k):
+            raise ValueError(f"depth[{k}] must be [B,1,{H >> k},{W >> k}], got {tuple(d.shape)}")
+    dev = tgt.device
+    for t in tensors:
+        if t.device.type != "cuda":
+            raise ValueError("photometric_loss is CUDA-only (no CPU fallback): move inputs to a B200")
+        if t.device != dev:
+            raise ValueError("all inputs must live on the same device")
+        if t.dtype != torch.float32:
+            raise TypeError("all inputs must be float32")
+        if not t.is_contiguous():
+            raise ValueError("inputs must be contiguous (NCHW); call .contiguous() outside the timed path")
+    return B, N, S, H, W
+
+
+class _Workspace:
+    """One scratch buffer per (device, stream), grown on demand; never shared across streams."""
+
+    _bufs = {}
+
+    @classmethod
+    def get(cls, nbytes: int, device: torch.device) -> torch.Tensor:
+        key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+        buf = cls._bufs.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+            cls._bufs[key] = buf
+        return buf
+
+
+class _PhotoLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pose, K, tgt, srcs, alpha, smooth_weight, lcc, lcc_detach, want_valid, *depth):
+        B, N, S, H, W = _check_inputs(depth, pose, K, tgt, srcs)
+        lib = _lib.load()
+        dev = tgt.device
+        needs_grad = any(ctx.needs_input_grad[i] for i in (0, 3)) or any(ctx.needs_input_grad[9:])
+        flags = (_lib.F_LCC if lcc else 0) | (_lib.F_LCC_DETACH if lcc_detach else 0)
+        if needs_grad:
+            flags |= _lib.F_SAVE_FOR_BWD
+        desc = _lib.make_desc(B, N, S, H, W, flags, alpha, smooth_weight)
+        nbytes = ctypes.c_size_t()
+        _lib.check(lib.colvo_workspace_bytes(ctypes.byref(desc), ctypes.byref(nbytes)), "colvo_workspace_bytes")
+        nsaved = ctypes.c_size_t()
+        _lib.check(lib.colvo_saved_doubles(ctypes.byref(desc), ctypes.byref(nsaved)), "colvo_saved_doubles")
+        with torch.cuda.device(dev):
+            ws = _Workspace.get(nbytes.value, dev)
+            loss = torch.empty((), dtype=torch.float32, device=dev)
+            ab = torch.empty(B, N, S, 2, dtype=torch.float32, device=dev)
+            sel = torch.empty(B, S, H, W, dtype=torch.uint8, device=dev)
+            saved = torch.empty(nsaved.value, dtype=torch.float64, device=dev)
+            valid = torch.empty(B, N, S, H, W, dtype=torch.uint8, device=dev) if want_valid else None
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            rc = lib.colvo_photo_forward(
+                ctypes.byref(desc), tgt.data_ptr(), srcs.data_ptr(), _lib.ptr_array([d.data_ptr() for d in depth]),
+                K.data_ptr(), pose.data_ptr(), loss.data_ptr(), ab.data_ptr(),
+                valid.data_ptr() if valid is not None else None, sel.data_ptr(), saved.data_ptr(), ws.data_ptr(),
+                ws.numel(), stream)
+        _lib.check(rc, "colvo_photo_forward")
+        ctx.desc_args = (B, N, S, H, W, flags, alpha, smooth_weight)
+        ctx.n_depth = S
+        if needs_grad:
+            ctx.save_for_backward(pose, K, tgt, srcs, sel, saved, *depth)
+        ctx.mark_non_differentiable(ab, sel)
+        if valid is not None:
+            ctx.mark_non_differentiable(valid)
+            return loss, ab, sel, valid
+        return loss, ab, sel
+
+    @staticmethod
+    def backward(ctx, grad_loss, *unused):
+        pose, K, tgt, srcs, sel, saved = ctx.saved_tensors[:6]
+        depth = ctx.saved_tensors[6:]
+        B, N, S, H, W, flags, alpha, smooth_weight = ctx.desc_args
+        want_src = ctx.needs_input_grad[3]
+        if not want_src:
+            flags |= _lib.F_NO_SRC_GRAD
+        lib = _lib.load()
+        dev = tgt.device
+        desc = _lib.make_desc(B, N, S, H, W, flags, alpha, smooth_weight)
+        nbytes = ctypes.c_size_t()
+        _lib.check(lib.colvo_workspace_bytes(ctypes.byref(desc), ctypes.byref(nbytes)), "colvo_workspace_bytes")
+        with torch.cuda.device(dev):
+            ws = _Workspace.get(nbytes.value, dev)
+            go = grad_loss.to(torch.float32).contiguous()
+            grad_depth = [torch.empty_like(d) for d in depth]
+            grad_T = torch.empty_like(pose)
+            grad_srcs = torch.empty_like(srcs) if want_src else None
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            rc = lib.colvo_photo_backward(
+                ctypes.byref(desc), tgt.data_ptr(), srcs.data_ptr(), _lib.ptr_array([d.data_ptr() for d in depth]),
+                K.data_ptr(), pose.data_ptr(), go.data_ptr(), sel.data_ptr(), saved.data_ptr(),
+                _lib.ptr_array([g.data_ptr() for g in grad_depth]), grad_T.data_ptr(),
+                grad_srcs.data_ptr() if want_src else None, ws.data_ptr(), ws.numel(), stream)
+        _lib.check(rc, "colvo_photo_backward")
+        gd = [g if ctx.needs_input_grad[9 + i] else None for i, g in enumerate(grad_depth)]
+        return (grad_T if ctx.needs_input_grad[0] else None, None, None, grad_srcs, None, None, None, None, None, *gd)
+
+
+def photometric_loss(
+    depth: Sequence[torch.Tensor],
+    pose: torch.Tensor,
+    K: torch.Tensor,
+    tgt: torch.Tensor,
+    srcs: torch.Tensor,
+    *,
+    alpha: float = 0.85,
+    smooth_weight: float = 1e-3,
+    lcc: bool = True,
+    lcc_detach: bool = False,
+    return_masks: bool = False,
+):
+    """View-synthesis photometric loss with LCC, min-reprojection / auto-mask and edge-aware
+    smoothness over S scales and N neighbouring frames.
+
+    depth: S tensors `[B,1,H>>k,W>>k]`; pose `[B,N,4,4]` (T target->source); K `[B,3,3]`;
+    tgt `[B,3,H,W]`; srcs `[B,N,3,H,W]`.  All CUDA, fp32, contiguous.  Differentiable in
+    depth, pose and srcs; K and tgt get no gradient (oracle A14).
+
+    Returns the 0-dim loss, or `(loss, valid u8 [B,N,S,H,W], sel u8 [B,S,H,W], ab [B,N,S,2])`.
+    """
+    out = _PhotoLossFn.apply(pose, K, tgt, srcs, float(alpha), float(smooth_weight), bool(lcc), bool(lcc_detach),
+                             bool(return_masks), *depth)
+    if return_masks:
+        loss, ab, sel, valid = out
+        return loss, valid, sel, ab
+    return out[0]
+
+
+class HostStepper:
+    """End-to-end step on pinned HOST buffers through `colvo_photo_step_host`: H2D of the inputs,
+    forward, backward (grad_loss = 1), D2H of the loss and gradients, all on one stream.  This is
+    the call `bench.py` times for the `e2e` number."""
+
+    def __init__(self, B, N, S, H, W, *, device="cuda:0", lcc=True, lcc_detach=False, want_src_grad=True,
+                 alpha=0.85, smooth_weight=1e-3):
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        flags = (_lib.F_LCC if lcc else 0) | (_lib.F_LCC_DETACH if lcc_detach else 0)
+        if not want_src_grad:
+            flags |= _lib.F_NO_SRC_GRAD
+        self.desc = _lib.make_desc(B, N, S, H, W, flags, alpha, smooth_weight)
+        n = ctypes.c_size_t()
+        _lib.check(self.lib.colvo_step_host_arena_bytes(ctypes.byref(self.desc), ctypes.byref(n)), "arena_bytes")
+        self.arena = torch.empty(n.value, dtype=torch.uint8, device=self.device)
+        pin = dict(dtype=torch.float32, pin_memory=True)
+        self.h_loss = torch.zeros(1, **pin)
+        self.h_grad_depth = [torch.zeros(B, 1, H >> k, W >> k, **pin) for k in range(S)]
+        self.h_grad_T = torch.zeros(B, N, 4, 4, **pin)
+        self.h_grad_srcs = torch.zeros(B, N, 3, H, W, **pin) if want_src_grad else None
+        self.S = S
+
+    def h2d_bytes(self, depth, pose, K, tgt, srcs) -> int:
+        return 4 * (tgt.numel() + srcs.numel() + sum(d.numel() for d in depth) + K.numel() + pose.numel())
+
+    def d2h_bytes(self) -> int:
+        n = 1 + sum(g.numel() for g in self.h_grad_depth) + self.h_grad_T.numel()
+        if self.h_grad_srcs is not None:
+            n += self.h_grad_srcs.numel()
+        return 4 * n
+
+    def step(self, depth, pose, K, tgt, srcs, stream: Optional[torch.cuda.Stream] = None):
+        """Inputs are CPU tensors (pinned for full speed).  Enqueues everything on `stream`; the
+        host outputs are valid after `stream.synchronize()`."""
+        for t in list(depth) + [pose, K, tgt, srcs]:
+            if t.device.type != "cpu" or t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError("HostStepper.step takes contiguous float32 CPU tensors")
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        with torch.cuda.device(self.device):
+            rc = self.lib.colvo_photo_step_host(
+                ctypes.byref(self.desc), tgt.data_ptr(), srcs.data_ptr(), _lib.ptr_array([d.data_ptr() for d in depth]),
+                K.data_ptr(), pose.data_ptr(), self.h_loss.data_ptr(),
+                _lib.ptr_array([g.data_ptr() for g in self.h_grad_depth]), self.h_grad_T.data_ptr(),
+                self.h_grad_srcs.data_ptr() if self.h_grad_srcs is not None else None, self.arena.data_ptr(),
+                self.arena.numel(), st.cuda_stream)
+        _lib.check(rc, "colvo_photo_step_host")
+        return self.h_loss

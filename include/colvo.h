@@ -1,0 +1,125 @@
+/* colvo.h -- C ABI of the B200-native ColVO photometric-loss path (libcolvo_b200.so).
+ *
+ * Drop-in boundary for the data-parallel hot path of HNUicda/CoIVO ("ColVO"): the
+ * per-pixel view-synthesis photometric loss that couples depth and pose
+ * (/root/reference/README.md:7 "loss function constraints to couple depth and pose
+ * estimation modes ... alignment of geometric projections between consecutive frames";
+ * "LCC ... recalibrating the luminosity values of adjacent frames").
+ *
+ * The upstream repository ships no source, hence no FFI to mirror: every entry point below
+ * cites the README sentence and the SURVEY.md section 8 row it implements, and
+ * INTEGRATION.md shows the ctypes binding a maintainer of a PyTorch training loop adds.
+ *
+ * Conventions:
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary;
+ *   - every tensor is fp32, contiguous NCHW, in DEVICE memory unless the name says host;
+ *   - the caller owns every buffer including the workspace; the library never allocates
+ *     device memory, never retains a pointer, never synchronises the device;
+ *   - all work is enqueued on the given cudaStream_t (passed as void*); calls are
+ *     CUDA-graph capturable and re-entrant on disjoint buffers;
+ *   - return value: 0 = success, >0 = a cudaError_t, <0 = a COLVO_E_* code;
+ *     colvo_error_string() explains either.
+ */
+#ifndef COLVO_H_
+#define COLVO_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define COLVO_VERSION 100          /* major*10000 + minor*100 + patch  (0.1.0) */
+#define COLVO_MAX_SCALES 4
+#define COLVO_MAX_SOURCES 2
+
+/* flags */
+#define COLVO_F_LCC 1u             /* apply the LCC brightness calibration (README.md:5,7)     */
+#define COLVO_F_LCC_DETACH 2u      /* do not differentiate through (a, b)                       */
+#define COLVO_F_SAVE_FOR_BWD 4u    /* forward also produces what colvo_photo_backward needs     */
+#define COLVO_F_NO_SRC_GRAD 8u     /* backward: skip the scatter-add into grad_srcs             */
+
+/* negative error codes */
+#define COLVO_E_BAD_DESC (-1)
+#define COLVO_E_WORKSPACE (-2)
+#define COLVO_E_NULL_PTR (-3)
+#define COLVO_E_MISALIGNED (-4)
+#define COLVO_E_UNSUPPORTED (-5)
+
+/* Problem descriptor.  h[k] = H >> k, w[k] = W >> k must hold (oracle A1/A3). */
+typedef struct ColvoDesc {
+  int32_t B, N, S, H, W;           /* triplets, sources (1..2), scales (1..4), full resolution  */
+  int32_t h[COLVO_MAX_SCALES];
+  int32_t w[COLVO_MAX_SCALES];
+  float alpha;                     /* SSIM weight, 0.85                                          */
+  float c1, c2;                    /* SSIM constants 1e-4, 9e-4                                  */
+  float eps_proj;                  /* 1e-7 in iz = 1/(Z'+eps)                                    */
+  float eps_lcc;                   /* 1e-6 on the LCC variance                                   */
+  float eps_disp;                  /* 1e-7 on the mean inverse depth                             */
+  float z_min;                     /* 1e-3                                                       */
+  float smooth_weight;             /* 1e-3 (scaled by 2^-k per scale)                            */
+  uint32_t flags;
+} ColvoDesc;
+
+/* Fill a descriptor with the defaults of the path (oracle/photometric.py constants). */
+int colvo_desc_init(ColvoDesc* d, int32_t B, int32_t N, int32_t S, int32_t H, int32_t W, uint32_t flags);
+
+int colvo_version(void);
+const char* colvo_error_string(int rc);
+
+/* Scratch bytes colvo_photo_forward / colvo_photo_backward need (max of the two), and the
+ * number of doubles in the `saved` buffer the forward hands to the backward. */
+int colvo_workspace_bytes(const ColvoDesc* d, size_t* bytes);
+int colvo_saved_doubles(const ColvoDesc* d, size_t* count);
+
+/* Forward: SURVEY.md section 8(a) rows 0-10.
+ *   tgt [B,3,H,W]  srcs [B,N,3,H,W]  depth[k] [B,1,h_k,w_k]  K [B,3,3]  T [B,N,4,4]
+ *   loss  [1]                 (out)
+ *   ab    [B,N,S,2]           (out)  LCC gain/bias per warped frame and scale
+ *   valid [B,N,S,H,W] u8      (out, nullable)  bit-exact projection validity
+ *   sel   [B,S,H,W]   u8      (out; required with COLVO_F_SAVE_FOR_BWD, else nullable)
+ *   saved [colvo_saved_doubles] (out; required with COLVO_F_SAVE_FOR_BWD, else nullable)
+ */
+int colvo_photo_forward(const ColvoDesc* d, const float* tgt, const float* srcs, const float* const* depth,
+                        const float* K, const float* T, float* loss, float* ab, uint8_t* valid, uint8_t* sel,
+                        double* saved, void* ws, size_t ws_bytes, void* stream);
+
+/* Backward: SURVEY.md section 8(a) row 11.  Inputs as in the forward plus its sel / saved.
+ *   grad_loss  [1] device scalar (dL_total / dloss)
+ *   grad_depth[k] [B,1,h_k,w_k]   (out, overwritten)
+ *   grad_T     [B,N,4,4]          (out, overwritten; bottom row 0)
+ *   grad_srcs  [B,N,3,H,W]        (out, overwritten; nullable with COLVO_F_NO_SRC_GRAD)
+ * No gradient is produced for K or tgt (oracle A14).
+ */
+int colvo_photo_backward(const ColvoDesc* d, const float* tgt, const float* srcs, const float* const* depth,
+                         const float* K, const float* T, const float* grad_loss, const uint8_t* sel,
+                         const double* saved, float* const* grad_depth, float* grad_T, float* grad_srcs, void* ws,
+                         size_t ws_bytes, void* stream);
+
+/* Inference-time warp + LCC consistency sweep over a frame sequence (BASELINE config 5;
+ * README.md:29: depth maps are stitched along the trajectory -- this is the check that gates it).
+ *   frames [F,3,H,W]  depth [F,1,H,W]  T [F-1,4,4] (T_{t->t+1})  K [3,3] (k_per_pair = 0) or [F-1,3,3]
+ *   out    [F-1,4] = {mean pe over valid pixels, a, b, valid fraction}
+ * flags: COLVO_F_LCC honoured.  Workspace: colvo_consistency_workspace_bytes.
+ */
+int colvo_consistency_workspace_bytes(int32_t F, int32_t H, int32_t W, size_t* bytes);
+int colvo_consistency(int32_t F, int32_t H, int32_t W, uint32_t flags, const float* frames, const float* depth,
+                      const float* T, const float* K, int32_t k_per_pair, float* out, void* ws, size_t ws_bytes,
+                      void* stream);
+
+/* End-to-end step on HOST buffers: H2D copies of the inputs (use pinned memory), forward,
+ * backward with grad_loss = 1, D2H copies of loss and gradients, all on `stream`.
+ * `arena` is caller-owned DEVICE memory of colvo_step_host_arena_bytes bytes.
+ * h_grad_srcs may be NULL with COLVO_F_NO_SRC_GRAD.  The call does not synchronise: the host
+ * outputs are complete once `stream` has been synchronised.
+ */
+int colvo_step_host_arena_bytes(const ColvoDesc* d, size_t* bytes);
+int colvo_photo_step_host(const ColvoDesc* d, const float* h_tgt, const float* h_srcs, const float* const* h_depth,
+                          const float* h_K, const float* h_T, float* h_loss, float* const* h_grad_depth,
+                          float* h_grad_T, float* h_grad_srcs, void* arena, size_t arena_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COLVO_H_ */

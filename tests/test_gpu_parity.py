@@ -1,0 +1,174 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.  Needs a B200.
+
+Tolerances (BASELINE.json north_star): loss and gradients rel 1e-4 in fp32; `valid` bit-exact;
+`sel` equal outside near-ties (gradient parity is measured against the
+oracle run with the kernel's own arg-min decision and (a, b))."""
+import pytest
+import torch
+
+import coivo_b200
+from coivo_b200.synthetic import make_triplets, make_sequence
+from oracle import photometric as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL = 1e-4
+
+
+def relinf(a, b):
+    return (a.cpu() - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
+
+
+def run_cuda(d, **kw):
+    depth = [x.to(DEV).requires_grad_() for x in d["depth"]]
+    pose = d["pose"].to(DEV).requires_grad_()
+    srcs = d["srcs"].to(DEV).requires_grad_()
+    out = coivo_b200.photometric_loss(depth, pose, d["K"].to(DEV), d["tgt"].to(DEV), srcs, return_masks=True, **kw)
+    loss, valid, sel, ab = out
+    loss.backward()
+    torch.cuda.synchronize()
+    return loss, valid.cpu(), sel.cpu(), ab.cpu(), [x.grad.cpu() for x in depth], pose.grad.cpu(), srcs.grad.cpu()
+
+
+def check_against_oracle(d, **kw):
+    N, S = d["srcs"].shape[1], len(d["depth"])
+    loss, valid, sel, ab, gd, gT, gs = run_cuda(d, **kw)
+    with torch.no_grad():
+        l0, v0, s0, ab0 = O.photometric_loss(d["depth"], d["pose"], d["K"], d["tgt"], d["srcs"], return_masks=True, **kw)
+        gap = O.candidate_gap(d["depth"], d["pose"], d["K"], d["tgt"], d["srcs"], alpha=kw.get("alpha", 0.85),
+                              lcc=kw.get("lcc", True))
+    assert torch.equal(valid, v0), "valid mask must be bit-exact"
+    assert torch.allclose(ab, ab0, rtol=1e-5, atol=1e-6)
+    mism = sel != s0
+    assert (gap[mism] < 1e-5).all(), f"{int(mism.sum())} sel mismatches away from ties"
+    assert mism.float().mean().item() < 1e-3
+    assert abs(loss.item() - l0.item()) <= TOL * abs(l0.item()), (loss.item(), l0.item())
+    od = [x.clone().requires_grad_() for x in d["depth"]]
+    op = d["pose"].clone().requires_grad_()
+    osr = d["srcs"].clone().requires_grad_()
+    l1 = O.photometric_loss(od, op, d["K"], d["tgt"], osr, sel_override=sel, ab_override=ab, **kw)
+    l1.backward()
+    for k in range(S):
+        assert relinf(gd[k], od[k].grad) < TOL, f"grad_depth[{k}] {relinf(gd[k], od[k].grad)}"
+    assert relinf(gT[:, :, :3], op.grad[:, :, :3]) < TOL, f"grad_pose {relinf(gT, op.grad)}"
+    assert gT[:, :, 3].abs().max().item() == 0
+    assert relinf(gs, osr.grad) < TOL, f"grad_srcs {relinf(gs, osr.grad)}"
+
+
+@pytest.mark.parametrize("B,H,W,N,S", [
+    (1, 256, 320, 2, 1),      # BASELINE config 1
+    (2, 64, 96, 2, 4),
+    (1, 37, 53, 2, 4),        # ragged: neither a tile multiple nor divisible by 2^k
+    (3, 16, 24, 1, 2),        # single source
+    (1, 8, 40, 2, 3),         # one tile row
+])
+def test_parity_small(B, H, W, N, S):
+    check_against_oracle(make_triplets(B, H, W, N=N, S=S, seed=B + H))
+
+
+@pytest.mark.parametrize("kw", [dict(lcc=False), dict(lcc_detach=True), dict(alpha=0.5, smooth_weight=0.1),
+                                dict(smooth_weight=0.0)])
+def test_parity_flags(kw):
+    check_against_oracle(make_triplets(2, 48, 64, seed=21), **kw)
+
+
+def test_parity_config2_one_triplet_full_size():
+    # BASELINE config 2 shape (256x320, N=2, S=4) at a batch the oracle finishes in seconds
+    check_against_oracle(make_triplets(2, 256, 320, seed=0))
+
+
+def test_parity_highres_slice():
+    # BASELINE config 4 geometry (W = 1350 is not a multiple of 4/8/32; pyramid by floor), cropped in H
+    check_against_oracle(make_triplets(1, 136, 1350, seed=4))
+
+
+def test_identity_pose_edge_case():
+    # KAT-1 on the GPU: whole border rows/columns sit exactly on 0 and W-1 (zero coordinate gradient)
+    d = make_triplets(1, 32, 48, seed=9)
+    d["pose"] = torch.eye(4).reshape(1, 1, 4, 4).repeat(1, 2, 1, 1).contiguous()
+    check_against_oracle(d)
+
+
+def test_behind_camera_all_invalid():
+    d = make_triplets(1, 32, 48, seed=10)
+    d["pose"][:, 0, 2, 3] = -5.0           # source 0: every point behind the camera -> n = 0 -> (a, b) = (1, 0)
+    loss, valid, sel, ab, gd, gT, gs = run_cuda(d)
+    assert valid[:, 0].sum().item() == 0
+    assert torch.equal(ab[:, 0], torch.tensor([1.0, 0.0]).expand_as(ab[:, 0]))
+    check_against_oracle(d)
+
+
+def test_no_grad_and_partial_grad_paths():
+    d = make_triplets(2, 32, 48, seed=12)
+    args = [[x.to(DEV) for x in d["depth"]], d["pose"].to(DEV), d["K"].to(DEV), d["tgt"].to(DEV), d["srcs"].to(DEV)]
+    with torch.no_grad():
+        l_ng = coivo_b200.photometric_loss(*args)
+    depth = [x.clone().requires_grad_() for x in args[0]]
+    l = coivo_b200.photometric_loss(depth, args[1], args[2], args[3], args[4])
+    l.backward()                              # srcs and pose do not require grad: scatter skipped
+    assert abs(l.item() - l_ng.item()) < 1e-7
+    od = [x.clone().requires_grad_() for x in d["depth"]]
+    O.photometric_loss(od, d["pose"], d["K"], d["tgt"], d["srcs"]).backward()
+    assert relinf(depth[0].grad, od[0].grad) < 5e-3      # without sel/ab override: near-tie noise only
+    # grad_loss scaling flows through
+    depth2 = [x.clone().requires_grad_() for x in args[0]]
+    (3.0 * coivo_b200.photometric_loss(depth2, args[1], args[2], args[3], args[4])).backward()
+    assert torch.allclose(depth2[1].grad, 3.0 * depth[1].grad, rtol=1e-5, atol=1e-12)
+
+
+def test_determinism_of_forward_and_non_scatter_grads():
+    d = make_triplets(2, 64, 96, seed=13)
+    a = run_cuda(d)
+    b = run_cuda(d)
+    assert a[0].item() == b[0].item()
+    assert torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
+    for x, y in zip(a[4], b[4]):
+        assert torch.equal(x, y)              # depth gradients use no atomics
+    assert torch.equal(a[5], b[5])            # pose gradients: fixed-order reduction
+    assert relinf(a[6], b[6]) < 1e-5          # grad_srcs: float REDG order is not fixed
+
+
+def test_full_size_properties_config2():
+    """BASELINE config 2 at full batch (12 x 256x320): size-independent properties instead of the oracle."""
+    d = make_triplets(12, 256, 320, seed=1)
+    loss, valid, sel, ab, gd, gT, gs = run_cuda(d)
+    assert torch.isfinite(loss) and loss.item() > 0
+    # batch-shard additivity: loss(B) == mean of the two half-batch losses
+    halves = []
+    for s in (slice(0, 6), slice(6, 12)):
+        sub = {k: ([x[s].contiguous() for x in v] if isinstance(v, list) else v[s].contiguous()) for k, v in d.items()}
+        halves.append(run_cuda(sub))
+    assert abs(loss.item() - 0.5 * (halves[0][0].item() + halves[1][0].item())) < 2e-6
+    assert torch.equal(valid[:6], halves[0][1]) and torch.equal(sel[6:], halves[1][2])
+    # gradients of a batch mean: each half's gradient is twice the full-batch one on its samples
+    assert relinf(2 * gd[0][:6], halves[0][4][0]) < 1e-5
+    # sum of grad_srcs over a source frame equals the analytic dL/db-type invariant: finite and bounded
+    assert torch.isfinite(gs).all() and torch.isfinite(gT).all()
+
+
+def test_consistency_sweep_matches_oracle():
+    s = make_sequence(9, 64, 80, seed=2)
+    got = coivo_b200.consistency(s["depth"].to(DEV), s["pose"].to(DEV), s["K"].to(DEV), s["frames"].to(DEV)).cpu()
+    ref = O.consistency(s["depth"], s["pose"], s["K"], s["frames"])
+    assert torch.allclose(got[:, 3], ref[:, 3], atol=0, rtol=0), "valid fraction comes from the bit-exact mask"
+    assert torch.allclose(got[:, 1:3], ref[:, 1:3], rtol=1e-5, atol=1e-6)
+    assert torch.allclose(got[:, 0], ref[:, 0], rtol=1e-4, atol=1e-7)
+    Kp = s["K"].reshape(1, 3, 3).repeat(8, 1, 1).contiguous()
+    got2 = coivo_b200.consistency(s["depth"].to(DEV), s["pose"].to(DEV), Kp.to(DEV), s["frames"].to(DEV), lcc=False).cpu()
+    ref2 = O.consistency(s["depth"], s["pose"], Kp, s["frames"], lcc=False)
+    assert torch.allclose(got2, ref2, rtol=1e-4, atol=1e-6)
+
+
+def test_host_stepper_matches_device_path():
+    d = make_triplets(2, 64, 96, seed=14)
+    st = coivo_b200.HostStepper(2, 2, 4, 64, 96, device=DEV)
+    pin = lambda t: t.pin_memory()
+    h = st.step([pin(x) for x in d["depth"]], pin(d["pose"]), pin(d["K"]), pin(d["tgt"]), pin(d["srcs"]))
+    torch.cuda.synchronize()
+    loss, valid, sel, ab, gd, gT, gs = run_cuda(d)
+    assert abs(h.item() - loss.item()) < 1e-7
+    for k in range(4):
+        assert torch.equal(st.h_grad_depth[k], gd[k])
+    assert torch.equal(st.h_grad_T, gT)
+    assert relinf(st.h_grad_srcs, gs) < 1e-5
+    assert st.d2h_bytes() == 4 * (1 + sum(x.numel() for x in gd) + gT.numel() + gs.numel())
