@@ -96,8 +96,15 @@ _SIGS = {
     "colvo_step_host_arena_bytes": (ctypes.c_int, [ctypes.POINTER(ColvoDesc), ctypes.POINTER(ctypes.c_size_t)]),
     "colvo_photo_step_host": (ctypes.c_int, [ctypes.POINTER(ColvoDesc), _vp, _vp, ctypes.POINTER(_vp), _vp, _vp, _vp,
                                              ctypes.POINTER(_vp), _vp, _vp, _vp, ctypes.c_size_t, _vp]),
+    "colvo_debug_time_kernel": (ctypes.c_int, [ctypes.c_int, _vp, _vp]),
 }
 EXPORTS = tuple(_SIGS)
+
+K_PHOTO_FWD, K_PHOTO_BWD, K_WARP_STATS = 1, 2, 3
+# kernels launched by one forward + one backward (S > 1, LCC on); bench.py's gpu_launches
+KERNELS_FWD = ("k_tgt_pyramid", "k_disp_sum", "k_warp_stats", "k_lcc_solve", "k_photo_fwd", "k_smooth_fwd",
+               "k_finalize_fwd")
+KERNELS_BWD = ("k_photo_bwd", "k_pose_final", "k_depth_gather", "k_tgt_pyramid", "k_smooth_bwd_a", "k_smooth_bwd_b")
 
 
 def load(auto_build: bool = True) -> ctypes.CDLL:

@@ -9,6 +9,10 @@
 
 using namespace colvo;
 
+namespace colvo {
+KernelTimer g_timer = {0, nullptr, nullptr};
+}
+
 namespace {
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
@@ -70,8 +74,8 @@ size_t carve_fwd(const ColvoDesc* d, void* ws, FwdBuffers& F) {
   F.stat_part = c.take<double>(BNS * F.stat_chunks * 5);
   F.disp_part = c.take<double>(BS * kSmoothChunks);
   F.smooth_part = c.take<double>(BS * kSmoothChunks * 2);
-  F.loss_part = c.take<float>((size_t)d->B * tiles);
-  F.g_part = c.take<float>((size_t)d->B * tiles * d->N * kMaxS * 2);
+  F.loss_part = c.take<double>((size_t)d->B * tiles);
+  F.g_part = c.take<double>((size_t)d->B * tiles * d->N * kMaxS * 2);
   F.pyr[0] = nullptr;
   for (int k = 1; k < kMaxS; ++k) F.pyr[k] = (k < d->S) ? c.take<float>((size_t)d->B * 3 * d->h[k] * d->w[k]) : nullptr;
   return c.off;
@@ -86,7 +90,7 @@ size_t carve_bwd(const ColvoDesc* d, void* ws, BwdBuffers& Bw) {
   Bw.dDhat[0] = nullptr;
   for (int k = 1; k < kMaxS; ++k) Bw.pyr[k] = (k < d->S) ? c.take<float>((size_t)d->B * 3 * d->h[k] * d->w[k]) : nullptr;
   for (int k = 1; k < kMaxS; ++k) Bw.dDhat[k] = (k < d->S) ? c.take<float>((size_t)d->B * HW) : nullptr;
-  Bw.pose_part = c.take<float>((size_t)d->B * tiles * d->N * 12);
+  Bw.pose_part = c.take<double>((size_t)d->B * tiles * d->N * 12);
   for (int k = 0; k < kMaxS; ++k) Bw.s_field[k] = (k < d->S) ? c.take<float>((size_t)d->B * d->h[k] * d->w[k]) : nullptr;
   Bw.sd_part = c.take<double>(BS * kSmoothChunks);
   return c.off;
@@ -184,6 +188,15 @@ int colvo_photo_backward(const ColvoDesc* d, const float* tgt, const float* srcs
   for (int k = 0; k < d->S; ++k) P.depth[k] = depth[k];
   return (int)launch_backward(P, Bw, grad_loss, sel, saved, grad_depth, grad_T, want_src ? grad_srcs : nullptr,
                               static_cast<cudaStream_t>(stream));
+}
+
+int colvo_debug_time_kernel(int which, void* ev_start, void* ev_stop) {
+  if (which < 0 || which > 3) return COLVO_E_UNSUPPORTED;
+  if (which != 0 && (!ev_start || !ev_stop)) return COLVO_E_NULL_PTR;
+  g_timer.which = which;
+  g_timer.start = static_cast<cudaEvent_t>(ev_start);
+  g_timer.stop = static_cast<cudaEvent_t>(ev_stop);
+  return 0;
 }
 
 // ---- consistency sweep ----------------------------------------------------------------------

@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(kThreads, 2)
     k_photo_bwd(KP P, const float* __restrict__ grad_loss, const uint8_t* __restrict__ sel,
                 const double* __restrict__ saved, float* __restrict__ grad_d0, float* __restrict__ dD1,
                 float* __restrict__ dD2, float* __restrict__ dD3, float* __restrict__ grad_srcs,
-                float* __restrict__ pose_part) {
+                double* __restrict__ pose_part) {
   __shared__ float xs[3][kBH][kBW];
   __shared__ float ys[3][kBH][kBW];
   __shared__ float ymu[3][kCH][kCW];
@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(kThreads, 2)
   __shared__ float coef[9][kCH][kCW];
   __shared__ unsigned char sels[kMaxS][kCH][kCW];
   __shared__ float cst[NS][kMaxS][6];               // a, b, P, Q, mean_x, mean_y per warped frame
-  __shared__ float red[(kThreads / 32) * NS * 12];
+  __shared__ double red[(kThreads / 32) * NS * 12];
 
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
   const int b = blockIdx.z, x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
@@ -228,20 +228,19 @@ __global__ void __launch_bounds__(kThreads, 2)
     }
   }
 
-  // ---- per-tile pose-gradient partials ----
+  // ---- per-tile pose-gradient partials (fp64: sums of terms of both signs) ----
   const int blk = (b * P.tiles_y + blockIdx.y) * P.tiles_x + blockIdx.x;
   const int lane = tid & 31, wid = tid >> 5;
-  __syncthreads();
 #pragma unroll
   for (int n = 0; n < NS; ++n)
 #pragma unroll
     for (int j = 0; j < 12; ++j) {
-      float s = warp_sum(gp[n][j]);
+      double s = warp_sum((double)gp[n][j]);
       if (lane == 0) red[wid * (NS * 12) + n * 12 + j] = s;
     }
   __syncthreads();
   if (tid < NS * 12) {
-    float s = 0.f;
+    double s = 0.0;
 #pragma unroll
     for (int w = 0; w < kThreads / 32; ++w) s += red[w * (NS * 12) + tid];
     pose_part[(long long)blk * (NS * 12) + tid] = s;
@@ -251,14 +250,14 @@ __global__ void __launch_bounds__(kThreads, 2)
 // ------------------------------------------------------------------------------------------
 // grad_T[b,n] from the per-tile partials: one CTA per (b,n); warp w reduces entries w, w+8.
 __global__ void __launch_bounds__(kThreads)
-    k_pose_final(KP P, const float* __restrict__ pose_part, float* __restrict__ grad_T) {
+    k_pose_final(KP P, const double* __restrict__ pose_part, float* __restrict__ grad_T) {
   const int bn = blockIdx.x, b = bn / P.N, n = bn % P.N;
   const int tiles = P.tiles_x * P.tiles_y, nv = P.N * 12;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   for (int j = wid; j < 16; j += kThreads / 32) {
     if (j < 12) {
       double acc = 0.0;
-      for (int t = lane; t < tiles; t += 32) acc += (double)pose_part[((long long)b * tiles + t) * nv + n * 12 + j];
+      for (int t = lane; t < tiles; t += 32) acc += pose_part[((long long)b * tiles + t) * nv + n * 12 + j];
       acc = warp_sum(acc);
       if (lane == 0) {
         int row, col;
@@ -387,12 +386,15 @@ cudaError_t launch_backward(const KP& P, const BwdBuffers& Wk, const float* grad
     if (e != cudaSuccess) return e;
   }
   dim3 grid(P.tiles_x, P.tiles_y, P.B);
+  {
+  ScopedKernelTimer tm(2, st);
   if (P.N == 1)
     k_photo_bwd<1><<<grid, kThreads, 0, st>>>(P, grad_loss, sel, saved, grad_depth[0], Wk.dDhat[1], Wk.dDhat[2],
                                               Wk.dDhat[3], grad_srcs, Wk.pose_part);
   else
     k_photo_bwd<2><<<grid, kThreads, 0, st>>>(P, grad_loss, sel, saved, grad_depth[0], Wk.dDhat[1], Wk.dDhat[2],
                                               Wk.dDhat[3], grad_srcs, Wk.pose_part);
+  }
   k_pose_final<<<P.B * P.N, kThreads, 0, st>>>(P, Wk.pose_part, grad_T);
   if (P.S > 1) {
     int blocks = div_up(P.h[1] * P.w[1], kThreads);

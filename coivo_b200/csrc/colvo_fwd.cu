@@ -160,12 +160,12 @@ __device__ __forceinline__ float pe_own(const float (&xs)[3][kFH][kFW], const fl
 
 template <int NS>
 __global__ void __launch_bounds__(kThreads, 2)
-    k_photo_fwd(KP P, const float* __restrict__ ab, uint8_t* __restrict__ sel_out, float* __restrict__ loss_part,
-                float* __restrict__ g_part, int need_g) {
+    k_photo_fwd(KP P, const float* __restrict__ ab, uint8_t* __restrict__ sel_out, double* __restrict__ loss_part,
+                double* __restrict__ g_part, int need_g) {
   constexpr int NV = 1 + NS * kMaxS * 2;
   __shared__ float ys[3][kFH][kFW];
   __shared__ float xs[3][kFH][kFW];
-  __shared__ float red[(kThreads / 32) * NV];
+  __shared__ double red[(kThreads / 32) * NV];
 
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
   const int b = blockIdx.z, x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
@@ -269,24 +269,25 @@ __global__ void __launch_bounds__(kThreads, 2)
     }
   }
 
+  // Per-tile partials.  dL/da and dL/db are sums of large terms of both signs: reduce them in
+  // fp64 (each thread contributes at most one fp32 term per slot, so nothing is lost before).
   const int blk = (b * P.tiles_y + blockIdx.y) * P.tiles_x + blockIdx.x;
-  // thread i < NV writes its reduced value: slot 0 -> loss partial, the rest -> g_part
-  float out[1];
-  (void)out;
   {
     const int lane = tid & 31, wid = tid >> 5;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      float s = warp_sum(acc[i]);
-      if (lane == 0) red[wid * NV + i] = s;
+      if (i == 0 || need_g) {
+        double s = warp_sum((double)acc[i]);
+        if (lane == 0) red[wid * NV + i] = s;
+      }
     }
     __syncthreads();
-    if (tid < NV) {
-      float s = 0.f;
+    if (tid < NV && (tid == 0 || need_g)) {
+      double s = 0.0;
 #pragma unroll
       for (int w = 0; w < kThreads / 32; ++w) s += red[w * NV + tid];
       if (tid == 0) loss_part[blk] = s;
-      else if (need_g) g_part[(long long)blk * (NS * kMaxS * 2) + (tid - 1)] = s;
+      else g_part[(long long)blk * (NS * kMaxS * 2) + (tid - 1)] = s;
     }
   }
 }
@@ -340,7 +341,7 @@ __global__ void __launch_bounds__(kThreads)
 // ------------------------------------------------------------------------------------------
 // block 0: the scalar loss.  block 1 + bnk: G_a, G_b of warped frame bnk (dL/da, dL/db).
 __global__ void __launch_bounds__(kThreads)
-    k_finalize_fwd(KP P, const float* __restrict__ loss_part, const float* __restrict__ g_part,
+    k_finalize_fwd(KP P, const double* __restrict__ loss_part, const double* __restrict__ g_part,
                    const double* __restrict__ smooth_part, float* __restrict__ loss, double* __restrict__ saved,
                    int need_g) {
   __shared__ double sm[(kThreads / 32) * 2];
@@ -348,7 +349,7 @@ __global__ void __launch_bounds__(kThreads)
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (blockIdx.x == 0) {
     double acc = 0.0;
-    for (int i = threadIdx.x; i < P.B * tiles; i += kThreads) acc += (double)loss_part[i];
+    for (int i = threadIdx.x; i < P.B * tiles; i += kThreads) acc += loss_part[i];
     double s = warp_sum(acc);
     if (lane == 0) sm[wid] = s;
     __syncthreads();
@@ -378,9 +379,9 @@ __global__ void __launch_bounds__(kThreads)
   const int slot = (n * kMaxS + k) * 2;
   double acc[2] = {0.0, 0.0};
   for (int t = threadIdx.x; t < tiles; t += kThreads) {
-    const float* g = g_part + ((long long)b * tiles + t) * nv + slot;
-    acc[0] += (double)g[0];
-    acc[1] += (double)g[1];
+    const double* g = g_part + ((long long)b * tiles + t) * nv + slot;
+    acc[0] += g[0];
+    acc[1] += g[1];
   }
   for (int j = 0; j < 2; ++j) {
     double s = warp_sum(acc[j]);
@@ -498,14 +499,19 @@ cudaError_t launch_forward(const KP& P, const FwdBuffers& Wk, float* loss, float
   cudaError_t e = launch_tgt_pyramid(P, Wk.pyr, st);
   if (e != cudaSuccess) return e;
   k_disp_sum<<<dim3(kSmoothChunks, P.B * P.S), kThreads, 0, st>>>(P, Wk.disp_part);
-  if (lcc || valid)
+  if (lcc || valid) {
+    ScopedKernelTimer tm(3, st);
     k_warp_stats<<<dim3(Wk.stat_chunks, BNS), kThreads, 0, st>>>(P, Wk.stat_part, valid);
+  }
   k_lcc_solve<<<BNS, 32, 0, st>>>(P, Wk.stat_part, Wk.stat_chunks, ab, saved);
   dim3 grid(P.tiles_x, P.tiles_y, P.B);
-  if (P.N == 1)
-    k_photo_fwd<1><<<grid, kThreads, 0, st>>>(P, ab, sel, Wk.loss_part, Wk.g_part, need_g);
-  else
-    k_photo_fwd<2><<<grid, kThreads, 0, st>>>(P, ab, sel, Wk.loss_part, Wk.g_part, need_g);
+  {
+    ScopedKernelTimer tm(1, st);
+    if (P.N == 1)
+      k_photo_fwd<1><<<grid, kThreads, 0, st>>>(P, ab, sel, Wk.loss_part, Wk.g_part, need_g);
+    else
+      k_photo_fwd<2><<<grid, kThreads, 0, st>>>(P, ab, sel, Wk.loss_part, Wk.g_part, need_g);
+  }
   double* saved_mean = saved ? saved + (long long)BNS * kSavedPerFrame : nullptr;
   k_smooth_fwd<<<dim3(kSmoothChunks, P.B * P.S), kThreads, 0, st>>>(P, Wk.disp_part, Wk.pyr[1], Wk.pyr[2], Wk.pyr[3],
                                                                      Wk.smooth_part, saved_mean);

@@ -128,15 +128,29 @@ struct FwdBuffers {
   float* pyr[kMaxS];     // target pyramid, k >= 1: [B,3,h_k,w_k]
   double* disp_part;     // [B*S][kSmoothChunks]
   double* smooth_part;   // [B*S][kSmoothChunks][2]
-  float* loss_part;      // [B*tiles]
-  float* g_part;         // [B*tiles][N*S*2]
+  double* loss_part;     // [B*tiles]
+  double* g_part;        // [B*tiles][N*kMaxS*2]
 };
 struct BwdBuffers {
   float* pyr[kMaxS];     // target pyramid (rebuilt: the forward's scratch is not kept alive)
   float* dDhat[kMaxS];   // k >= 1: [B,H,W] full-resolution depth adjoint before the up-sample adjoint
-  float* pose_part;      // [B*tiles][N*12]
+  double* pose_part;     // [B*tiles][N*12]
   float* s_field[kMaxS]; // smoothness adjoint dL/dd* per pixel, [B,h_k,w_k]
   double* sd_part;       // [B*S][kSmoothChunks]
+};
+
+// one-shot event bracket around one kernel launch (colvo_debug_time_kernel)
+struct KernelTimer { int which; cudaEvent_t start, stop; };
+extern KernelTimer g_timer;   // process-wide: autograd runs the backward on its own thread
+struct ScopedKernelTimer {
+  bool on;
+  cudaStream_t st;
+  ScopedKernelTimer(int id, cudaStream_t s) : on(g_timer.which == id), st(s) {
+    if (on) cudaEventRecord(g_timer.start, st);
+  }
+  ~ScopedKernelTimer() {
+    if (on) { cudaEventRecord(g_timer.stop, st); g_timer.which = 0; }
+  }
 };
 
 cudaError_t launch_tgt_pyramid(const KP& P, float* const* pyr, cudaStream_t st);

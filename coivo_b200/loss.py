@@ -43,14 +43,15 @@ def _check_inputs(depth, pose, K, tgt, srcs):
     for k, d in enumerate(depth):
         if tuple(d.shape) != (B, 1, H >> k, W >> k):
             raise ValueError(f"depth[{k}] must be [B,1,{H >> k},{W >> k}], got {tuple(d.shape)}")
+    for t in tensors:
+        if t.dtype != torch.float32:
+            raise TypeError("all inputs must be float32")
     dev = tgt.device
     for t in tensors:
         if t.device.type != "cuda":
             raise ValueError("photometric_loss is CUDA-only (no CPU fallback): move inputs to a B200")
         if t.device != dev:
             raise ValueError("all inputs must live on the same device")
-        if t.dtype != torch.float32:
-            raise TypeError("all inputs must be float32")
         if not t.is_contiguous():
             raise ValueError("inputs must be contiguous (NCHW); call .contiguous() outside the timed path")
     return B, N, S, H, W

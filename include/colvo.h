@@ -119,6 +119,15 @@ int colvo_photo_step_host(const ColvoDesc* d, const float* h_tgt, const float* h
                           const float* h_K, const float* h_T, float* h_loss, float* const* h_grad_depth,
                           float* h_grad_T, float* h_grad_srcs, void* arena, size_t arena_bytes, void* stream);
 
+/* Profiling aid (bench.py's roofline leg): bracket the NEXT launch of one kernel with two
+ * caller-owned cudaEvent_t on the launching stream.  One-shot, process-wide; pass
+ * which = 0 to clear.  Not for use under CUDA-graph capture.
+ *   which: 1 = k_photo_fwd, 2 = k_photo_bwd, 3 = k_warp_stats */
+#define COLVO_K_PHOTO_FWD 1
+#define COLVO_K_PHOTO_BWD 2
+#define COLVO_K_WARP_STATS 3
+int colvo_debug_time_kernel(int which, void* ev_start, void* ev_stop);
+
 #ifdef __cplusplus
 }
 #endif
