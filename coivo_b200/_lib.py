@@ -102,9 +102,8 @@ EXPORTS = tuple(_SIGS)
 
 K_PHOTO_FWD, K_PHOTO_BWD, K_WARP_STATS = 1, 2, 3
 # kernels launched by one forward + one backward (S > 1, LCC on); bench.py's gpu_launches
-KERNELS_FWD = ("k_tgt_pyramid", "k_disp_sum", "k_warp_stats", "k_lcc_solve", "k_photo_fwd", "k_smooth_fwd",
-               "k_finalize_fwd")
-KERNELS_BWD = ("k_photo_bwd", "k_pose_final", "k_depth_gather", "k_tgt_pyramid", "k_smooth_bwd_a", "k_smooth_bwd_b")
+KERNELS_FWD = ("k_prepass", "k_warp_stats", "k_lcc_solve", "k_photo_fwd", "k_smooth_fwd", "k_finalize_fwd")
+KERNELS_BWD = ("k_photo_bwd", "k_pose_final", "k_depth_gather")
 
 
 def load(auto_build: bool = True) -> ctypes.CDLL:

@@ -62,6 +62,10 @@ void fill_params(KP& P, const ColvoDesc* d) {
   P.K_bs = 9; P.T_ns = 16; P.T_bs = 16 * d->N;
   P.tiles_x = div_up(d->W, kTileW);
   P.tiles_y = div_up(d->H, kTileH);
+  for (int k = 0; k < d->S; ++k) {
+    int c = div_up(d->h[k] * d->w[k], kSmoothPixPerBlock);
+    P.sm_chunks[k] = c < 1 ? 1 : (c > kSmoothMaxChunks ? kSmoothMaxChunks : c);
+  }
 }
 
 int stat_chunks(const ColvoDesc* d) { return div_up(d->H * d->W, kThreads * kStatPPT); }
@@ -72,8 +76,8 @@ size_t carve_fwd(const ColvoDesc* d, void* ws, FwdBuffers& F) {
   const size_t tiles = (size_t)div_up(d->W, kTileW) * div_up(d->H, kTileH);
   F.stat_chunks = stat_chunks(d);
   F.stat_part = c.take<double>(BNS * F.stat_chunks * 5);
-  F.disp_part = c.take<double>(BS * kSmoothChunks);
-  F.smooth_part = c.take<double>(BS * kSmoothChunks * 2);
+  F.disp_part = c.take<double>(BS * kSmoothMaxChunks);
+  F.smooth_part = c.take<double>(BS * kSmoothMaxChunks * 3);
   F.loss_part = c.take<double>((size_t)d->B * tiles);
   F.g_part = c.take<double>((size_t)d->B * tiles * d->N * kMaxS * 2);
   F.pyr[0] = nullptr;
@@ -83,17 +87,31 @@ size_t carve_fwd(const ColvoDesc* d, void* ws, FwdBuffers& F) {
 
 size_t carve_bwd(const ColvoDesc* d, void* ws, BwdBuffers& Bw) {
   Carver c(ws);
-  const size_t BS = (size_t)d->B * d->S;
   const size_t tiles = (size_t)div_up(d->W, kTileW) * div_up(d->H, kTileH);
   const size_t HW = (size_t)d->H * d->W;
-  Bw.pyr[0] = nullptr;
   Bw.dDhat[0] = nullptr;
-  for (int k = 1; k < kMaxS; ++k) Bw.pyr[k] = (k < d->S) ? c.take<float>((size_t)d->B * 3 * d->h[k] * d->w[k]) : nullptr;
   for (int k = 1; k < kMaxS; ++k) Bw.dDhat[k] = (k < d->S) ? c.take<float>((size_t)d->B * HW) : nullptr;
   Bw.pose_part = c.take<double>((size_t)d->B * tiles * d->N * 12);
-  for (int k = 0; k < kMaxS; ++k) Bw.s_field[k] = (k < d->S) ? c.take<float>((size_t)d->B * d->h[k] * d->w[k]) : nullptr;
-  Bw.sd_part = c.take<double>(BS * kSmoothChunks);
   return c.off;
+}
+
+// the caller-owned `saved` buffer: doubles first, then the fp32 smoothness adjoint fields
+size_t carve_saved(const ColvoDesc* d, double* saved, SavedView& sv) {
+  const size_t BNS = (size_t)d->B * d->N * d->S, BS = (size_t)d->B * d->S;
+  size_t nd = BNS * kSavedPerFrame + BS * kSavedPerScale;
+  sv.frame = saved;
+  sv.scale = saved ? saved + BNS * kSavedPerFrame : nullptr;
+  float* f = saved ? reinterpret_cast<float*>(saved + nd) : nullptr;
+  size_t nf = 0;
+  for (int k = 0; k < kMaxS; ++k) {
+    if (k < d->S) {
+      sv.s_field[k] = f ? f + nf : nullptr;
+      nf += (size_t)d->B * d->h[k] * d->w[k];
+    } else {
+      sv.s_field[k] = nullptr;
+    }
+  }
+  return nd + (nf + 1) / 2;
 }
 
 __global__ void k_fill_one(float* p) { *p = 1.0f; }
@@ -144,7 +162,8 @@ int colvo_saved_doubles(const ColvoDesc* d, size_t* count) {
   int rc = check_desc(d);
   if (rc) return rc;
   if (!count) return COLVO_E_NULL_PTR;
-  *count = (size_t)d->B * d->N * d->S * kSavedPerFrame + (size_t)d->B * d->S;
+  SavedView sv;
+  *count = carve_saved(d, nullptr, sv);
   return 0;
 }
 
@@ -164,7 +183,9 @@ int colvo_photo_forward(const ColvoDesc* d, const float* tgt, const float* srcs,
   fill_params(P, d);
   P.tgt = tgt; P.srcs = srcs; P.K = K; P.T = T;
   for (int k = 0; k < d->S; ++k) P.depth[k] = depth[k];
-  return (int)launch_forward(P, F, loss, ab, valid, sel, saved, static_cast<cudaStream_t>(stream));
+  SavedView sv;
+  carve_saved(d, (d->flags & COLVO_F_SAVE_FOR_BWD) ? saved : nullptr, sv);
+  return (int)launch_forward(P, F, loss, ab, valid, sel, sv, static_cast<cudaStream_t>(stream));
 }
 
 int colvo_photo_backward(const ColvoDesc* d, const float* tgt, const float* srcs, const float* const* depth,
@@ -186,7 +207,9 @@ int colvo_photo_backward(const ColvoDesc* d, const float* tgt, const float* srcs
   fill_params(P, d);
   P.tgt = tgt; P.srcs = srcs; P.K = K; P.T = T;
   for (int k = 0; k < d->S; ++k) P.depth[k] = depth[k];
-  return (int)launch_backward(P, Bw, grad_loss, sel, saved, grad_depth, grad_T, want_src ? grad_srcs : nullptr,
+  SavedView sv;
+  carve_saved(d, const_cast<double*>(saved), sv);
+  return (int)launch_backward(P, Bw, grad_loss, sel, sv, grad_depth, grad_T, want_src ? grad_srcs : nullptr,
                               static_cast<cudaStream_t>(stream));
 }
 

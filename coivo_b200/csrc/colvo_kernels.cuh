@@ -10,18 +10,23 @@ namespace colvo {
 constexpr int kMaxS = 4;
 constexpr int kMaxN = 2;
 constexpr int kThreads = 256;
-constexpr int kTileW = 32;     // one warp = one tile row: coalesced 128 B rows
+constexpr int kTileW = 32;       // one warp = one tile row: coalesced 128 B rows
 constexpr int kTileH = 8;
-constexpr int kStatPPT = 8;    // pixels per thread in the LCC statistics pass
-constexpr int kSmoothChunks = 16;
+constexpr int kStatPPT = 8;      // pixels per thread in the LCC statistics pass
+constexpr int kSmoothMaxChunks = 64;
+constexpr int kSmoothPixPerBlock = 2048;
 
-// saved[] layout (doubles): per (b,n,k) kSavedPerFrame values, then per (b,k) the mean inverse depth
-constexpr int kSavedPerFrame = 8;   // n, mean_x, mean_y, 1/(n (var+eps)), a, b, G_a, G_b
+// saved[] layout: doubles  [B*N*S][kSavedPerFrame]  n, mean_x, mean_y, 1/(n (var+eps)), a, b, G_a, G_b
+//                 doubles  [B*S][kSavedPerScale]    mean inverse depth, sum_p s_p d_p
+//                 floats   s-field of every scale   dL_smooth/dd*_p for grad_loss = 1, [B,h_k,w_k]
+constexpr int kSavedPerFrame = 8;
+constexpr int kSavedPerScale = 2;
 
 struct KP {
   int B, N, S, H, W, HW;
   int h[kMaxS], w[kMaxS];
   float ry[kMaxS], rx[kMaxS];        // h_k / H, w_k / W rounded once to fp32 (oracle._upsample_axis)
+  int sm_chunks[kMaxS];              // smoothness CTAs per (b, k)
   float alpha, c1, c2, eps_proj, eps_lcc, eps_disp, z_min, smooth_weight;
   unsigned flags;
   const float* tgt;                  // [B,3,H,W]
@@ -70,23 +75,24 @@ __device__ __forceinline__ float depth_at(const KP& P, const float* __restrict__
   return upsample_blend(d00, d01, d10, d11, ax.w1, ay.w1);
 }
 
-// Rows 1-4 for one pixel: geometry, taps and the three raw warped channel values.
+// Rows 1-4 for one pixel whose ray (rx, ry) and up-sampled depth D are already known (both are
+// shared by the N sources; the ray also by the S scales): geometry, taps, 12 texels, 3 channels.
+// `src` is the [3][H][W] plane set of one source frame; offsets stay 32-bit (3*HW < 2^31).
 struct Texels { float i00[3], i01[3], i10[3], i11[3]; };
-__device__ __forceinline__ void warp_pixel(const KP& P, const float* __restrict__ Dk, int k,
-                                           const float* __restrict__ src, const Cam& cam, const Pose& pose, int px,
-                                           int py, Geo& g, Taps& t, Texels& tx, float (&x)[3]) {
-  float D = depth_at(P, Dk, k, px, py);
-  g = reproject(px, py, D, cam, pose, P.W, P.H, P.eps_proj, P.z_min);
+__device__ __forceinline__ void warp_sample(const KP& P, const float* __restrict__ src, const Cam& cam,
+                                            const Pose& pose, float rx, float ry, float D, Geo& g, Taps& t,
+                                            Texels& tx, float (&x)[3]) {
+  g = reproject_ray(rx, ry, D, cam, pose, P.W, P.H, P.eps_proj, P.z_min);
   t = make_taps(g.u, g.v, P.W, P.H);
-  const int o00 = t.y0 * P.W + t.x0, o01 = t.y0 * P.W + t.x1;
-  const int o10 = t.y1 * P.W + t.x0, o11 = t.y1 * P.W + t.x1;
+  const int r0 = t.y0 * P.W, r1 = t.y1 * P.W;
+  const int o00 = r0 + t.x0, o01 = r0 + t.x1, o10 = r1 + t.x0, o11 = r1 + t.x1;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    const float* p = src + (long long)c * P.HW;
-    tx.i00[c] = __ldg(p + o00);
-    tx.i01[c] = __ldg(p + o01);
-    tx.i10[c] = __ldg(p + o10);
-    tx.i11[c] = __ldg(p + o11);
+    const int co = c * P.HW;
+    tx.i00[c] = __ldg(src + (co + o00));
+    tx.i01[c] = __ldg(src + (co + o01));
+    tx.i10[c] = __ldg(src + (co + o10));
+    tx.i11[c] = __ldg(src + (co + o11));
   }
 #pragma unroll
   for (int c = 0; c < 3; ++c) x[c] = bilerp(tx.i00[c], tx.i01[c], tx.i10[c], tx.i11[c], t.wx, t.wy);
@@ -126,17 +132,19 @@ struct FwdBuffers {
   double* stat_part;     // [B*N*S][stat_chunks][5]
   int stat_chunks;
   float* pyr[kMaxS];     // target pyramid, k >= 1: [B,3,h_k,w_k]
-  double* disp_part;     // [B*S][kSmoothChunks]
-  double* smooth_part;   // [B*S][kSmoothChunks][2]
+  double* disp_part;     // [B*S][kSmoothMaxChunks]
+  double* smooth_part;   // [B*S][kSmoothMaxChunks][3]   sum_x, sum_y, sum s*d
   double* loss_part;     // [B*tiles]
   double* g_part;        // [B*tiles][N*kMaxS*2]
 };
 struct BwdBuffers {
-  float* pyr[kMaxS];     // target pyramid (rebuilt: the forward's scratch is not kept alive)
   float* dDhat[kMaxS];   // k >= 1: [B,H,W] full-resolution depth adjoint before the up-sample adjoint
   double* pose_part;     // [B*tiles][N*12]
-  float* s_field[kMaxS]; // smoothness adjoint dL/dd* per pixel, [B,h_k,w_k]
-  double* sd_part;       // [B*S][kSmoothChunks]
+};
+struct SavedView {       // the caller-owned `saved` buffer, carved
+  double* frame;         // [B*N*S][kSavedPerFrame]
+  double* scale;         // [B*S][kSavedPerScale]
+  float* s_field[kMaxS]; // [B,h_k,w_k]
 };
 
 // one-shot event bracket around one kernel launch (colvo_debug_time_kernel)
@@ -153,11 +161,10 @@ struct ScopedKernelTimer {
   }
 };
 
-cudaError_t launch_tgt_pyramid(const KP& P, float* const* pyr, cudaStream_t st);
 cudaError_t launch_forward(const KP& P, const FwdBuffers& W, float* loss, float* ab, uint8_t* valid, uint8_t* sel,
-                           double* saved, cudaStream_t st);
+                           const SavedView& saved, cudaStream_t st);
 cudaError_t launch_backward(const KP& P, const BwdBuffers& W, const float* grad_loss, const uint8_t* sel,
-                            const double* saved, float* const* grad_depth, float* grad_T, float* grad_srcs,
+                            const SavedView& saved, float* const* grad_depth, float* grad_T, float* grad_srcs,
                             cudaStream_t st);
 cudaError_t launch_consistency(const KP& P, double* stat_part, int stat_chunks, double* pe_part, float* ab,
                                float* out, cudaStream_t st);

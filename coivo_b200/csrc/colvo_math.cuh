@@ -27,6 +27,7 @@ CV_HD float p_mul(float a, float b) { return __fmul_rn(a, b); }
 CV_HD float p_div(float a, float b) { return __fdiv_rn(a, b); }
 CV_HD float p_rcp(float a) { return __frcp_rn(a); }
 CV_HD float f_fma(float a, float b, float c) { return fmaf(a, b, c); }
+CV_HD float f_rcp(float a) { return __fdividef(1.0f, a); }   // approximate (MUFU.RCP): SSIM only, never the pinned chain
 #else
 // host build: compiled with -ffp-contract=off, so each operator rounds once
 CV_HD float p_add(float a, float b) { volatile float r = a + b; return r; }
@@ -35,6 +36,7 @@ CV_HD float p_mul(float a, float b) { volatile float r = a * b; return r; }
 CV_HD float p_div(float a, float b) { volatile float r = a / b; return r; }
 CV_HD float p_rcp(float a) { volatile float r = 1.0f / a; return r; }
 CV_HD float f_fma(float a, float b, float c) { return a * b + c; }
+CV_HD float f_rcp(float a) { return 1.0f / a; }
 #endif
 
 CV_HD int imin(int a, int b) { return a < b ? a : b; }
@@ -78,10 +80,13 @@ struct Geo {
   float iz;          // 1 / (Z' + eps)
   bool valid;
 };
-CV_HD Geo reproject(int px, int py, float D, const Cam& c, const Pose& p, int W, int H, float eps, float z_min) {
+// the ray of a pixel depends on the pixel and K only: kernels hoist it out of their (k, n) loops
+CV_HD float ray_x(int px, const Cam& c) { return p_div(p_sub((float)px, c.cx), c.fx); }
+CV_HD float ray_y(int py, const Cam& c) { return p_div(p_sub((float)py, c.cy), c.fy); }
+CV_HD Geo reproject_ray(float rx, float ry, float D, const Cam& c, const Pose& p, int W, int H, float eps, float z_min) {
   Geo g;
-  g.rx = p_div(p_sub((float)px, c.cx), c.fx);
-  g.ry = p_div(p_sub((float)py, c.cy), c.fy);
+  g.rx = rx;
+  g.ry = ry;
   g.X = p_mul(g.rx, D);
   g.Y = p_mul(g.ry, D);
   g.Z = D;
@@ -95,6 +100,9 @@ CV_HD Geo reproject(int px, int py, float D, const Cam& c, const Pose& p, int W,
   g.v = p_mul(y, g.iz);
   g.valid = (g.u >= 0.f) && (g.u <= (float)(W - 1)) && (g.v >= 0.f) && (g.v <= (float)(H - 1)) && (Zp > z_min);
   return g;
+}
+CV_HD Geo reproject(int px, int py, float D, const Cam& c, const Pose& p, int W, int H, float eps, float z_min) {
+  return reproject_ray(ray_x(px, c), ray_y(py, c), D, c, p, W, H, eps, z_min);
 }
 
 // ---- row 4: bilinear taps with border padding ----
@@ -141,7 +149,7 @@ CV_HD SsimParts ssim_parts(float mut, float st, float stxy, float muy, float sy,
   float A2 = 2.f * stxy + c2;
   float B1 = mut * mut + muy * muy + c1;
   float B2 = st + sy + c2;
-  float iB1 = 1.0f / B1, iB2 = 1.0f / B2;
+  float iB1 = f_rcp(B1), iB2 = f_rcp(B2);
   SsimParts o;
   float r2 = A2 * iB2;
   o.S = A1 * iB1 * r2;

@@ -51,7 +51,8 @@ def test_workspace_and_saved_sizes():
     assert lib.colvo_workspace_bytes(ctypes.byref(d), ctypes.byref(n)) == 0
     assert lib.colvo_saved_doubles(ctypes.byref(d), ctypes.byref(m)) == 0
     assert lib.colvo_step_host_arena_bytes(ctypes.byref(d), ctypes.byref(a)) == 0
-    assert m.value == 12 * 2 * 4 * 8 + 12 * 4
+    # doubles: 8 per warped frame + 2 per (b, k); then the fp32 smoothness adjoint fields (2 per double)
+    assert m.value == 12 * 2 * 4 * 8 + 12 * 4 * 2 + (12 * (256 * 320 + 128 * 160 + 64 * 80 + 32 * 40) + 1) // 2
     assert 1 << 20 < n.value < 64 << 20                      # tens of MB, not the 8x I_w cache
     assert a.value > n.value + 4 * 12 * (3 + 6 + 6) * 256 * 320
     assert lib.colvo_workspace_bytes(ctypes.byref(d), None) == -3

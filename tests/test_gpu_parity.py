@@ -30,7 +30,7 @@ def run_cuda(d, **kw):
     return loss, valid.cpu(), sel.cpu(), ab.cpu(), [x.grad.cpu() for x in depth], pose.grad.cpu(), srcs.grad.cpu()
 
 
-def check_against_oracle(d, **kw):
+def check_against_oracle(d, depth_atol=0.0, **kw):
     N, S = d["srcs"].shape[1], len(d["depth"])
     loss, valid, sel, ab, gd, gT, gs = run_cuda(d, **kw)
     with torch.no_grad():
@@ -40,7 +40,9 @@ def check_against_oracle(d, **kw):
     assert torch.equal(valid, v0), "valid mask must be bit-exact"
     assert torch.allclose(ab, ab0, rtol=1e-5, atol=1e-6)
     mism = sel != s0
-    assert (gap[mism] < 1e-5).all(), f"{int(mism.sum())} sel mismatches away from ties"
+    # fp32 SSIM: sigma = E[x^2] - mu^2 carries ~6e-8 absolute rounding against C2 = 9e-4, i.e. up to ~1e-4
+    # relative noise in pe on flat regions; a different arg-min is only legitimate inside that band
+    assert (gap[mism] < 1e-4).all(), f"{int(mism.sum())} sel mismatches away from ties"
     assert mism.float().mean().item() < 1e-3
     assert abs(loss.item() - l0.item()) <= TOL * abs(l0.item()), (loss.item(), l0.item())
     od = [x.clone().requires_grad_() for x in d["depth"]]
@@ -49,7 +51,8 @@ def check_against_oracle(d, **kw):
     l1 = O.photometric_loss(od, op, d["K"], d["tgt"], osr, sel_override=sel, ab_override=ab, **kw)
     l1.backward()
     for k in range(S):
-        assert relinf(gd[k], od[k].grad) < TOL, f"grad_depth[{k}] {relinf(gd[k], od[k].grad)}"
+        err = (gd[k] - od[k].grad).abs().max().item()
+        assert err < TOL * od[k].grad.abs().max().item() + depth_atol, f"grad_depth[{k}] {relinf(gd[k], od[k].grad)}"
     assert relinf(gT[:, :, :3], op.grad[:, :, :3]) < TOL, f"grad_pose {relinf(gT, op.grad)}"
     assert gT[:, :, 3].abs().max().item() == 0
     assert relinf(gs, osr.grad) < TOL, f"grad_srcs {relinf(gs, osr.grad)}"
@@ -86,7 +89,10 @@ def test_identity_pose_edge_case():
     # KAT-1 on the GPU: whole border rows/columns sit exactly on 0 and W-1 (zero coordinate gradient)
     d = make_triplets(1, 32, 48, seed=9)
     d["pose"] = torch.eye(4).reshape(1, 1, 4, 4).repeat(1, 2, 1, 1).contiguous()
-    check_against_oracle(d)
+    # With zero motion u' = rx*fx + cx does not depend on depth: the photometric depth gradient is an exact
+    # cancellation (terms ~5e-3, fp32 residue ~5e-10 on either side) on top of a ~5e-7 smoothness gradient,
+    # so the depth comparison carries an absolute floor here.
+    check_against_oracle(d, depth_atol=2e-9)
 
 
 def test_behind_camera_all_invalid():

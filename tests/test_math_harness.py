@@ -72,7 +72,7 @@ def test_harness_matches_oracle(harness, B, H, W, N, S, flags):
     assert torch.equal(valid, v0), "valid mask must be bit-exact"
     assert torch.allclose(ab, ab0, rtol=1e-5, atol=1e-6)
     mism = sel != s0
-    assert (gap[mism] < 1e-5).all(), "sel may differ only at near-ties"
+    assert (gap[mism] < 1e-4).all(), "sel may differ only at near-ties"
     assert abs(loss.item() - l0.item()) <= 1e-5 * abs(l0.item())
     l1 = O.photometric_loss(depth, pose, d["K"], d["tgt"], srcs, smooth_weight=0.0, lcc=lcc, lcc_detach=detach,
                             sel_override=sel, ab_override=ab)
