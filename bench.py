@@ -201,6 +201,12 @@ def run_ours(args):
     ms_total = e0.elapsed_time(e1)
     kern_ms = statistics.mean(a.elapsed_time(b_) for a, b_ in kev)
 
+    if args.profile:
+        if rank == 0:
+            print(json.dumps({"profile_run": True, "ms_per_step": ms_total / steps, "kernel_ms": kern_ms}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     # end-to-end leg: pinned host buffers -> H2D -> fwd -> bwd -> D2H, through the C ABI
     stepper = coivo_b200.HostStepper(B_PER_GPU, N_SRC, S, H, W, device=dev)
     hb = batches[0]["host"]
@@ -270,6 +276,7 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--profile", action="store_true", help="profiling run: skip the e2e and CPU-baseline legs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -13,7 +13,8 @@ from typing import List, Optional
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
-LIB_PATH = os.path.join(PKG_DIR, "libcolvo_b200.so")
+# COLVO_LIB selects another build of the same sources (tuning experiments); the default is the in-tree library
+LIB_PATH = os.environ.get("COLVO_LIB") or os.path.join(PKG_DIR, "libcolvo_b200.so")
 SOURCES = ["colvo_fwd.cu", "colvo_bwd.cu", "colvo_api.cu"]
 HEADERS = ["colvo_math.cuh", "colvo_kernels.cuh", os.path.join("..", "..", "include", "colvo.h")]
 
@@ -41,17 +42,19 @@ class ColvoDesc(ctypes.Structure):
     ]
 
 
-def nvcc_command(out: str = LIB_PATH) -> List[str]:
+def nvcc_command(out: str = LIB_PATH, defines=()) -> List[str]:
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     if not os.path.exists(nvcc):
         nvcc = "nvcc"
     return [
         nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
         "-Xcompiler", "-fPIC", "-shared", "-o", out,
-    ] + [os.path.join(CSRC, s) for s in SOURCES]
+    ] + ["-D" + d for d in defines] + [os.path.join(CSRC, s) for s in SOURCES]
 
 
 def needs_build() -> bool:
+    if os.environ.get("COLVO_LIB"):
+        return False
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)

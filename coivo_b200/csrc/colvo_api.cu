@@ -34,7 +34,7 @@ int check_desc(const ColvoDesc* d) {
   if (!d) return COLVO_E_NULL_PTR;
   if (d->B < 1 || d->N < 1 || d->N > COLVO_MAX_SOURCES || d->S < 1 || d->S > COLVO_MAX_SCALES) return COLVO_E_BAD_DESC;
   if (d->H < 2 || d->W < 2) return COLVO_E_BAD_DESC;
-  if ((long long)d->H * d->W > (1ll << 28)) return COLVO_E_BAD_DESC;
+  if ((long long)d->H * d->W > (1ll << 26)) return COLVO_E_BAD_DESC;   // 9 * HW element offsets stay 32-bit
   if (d->B > 65535) return COLVO_E_BAD_DESC;
   for (int k = 0; k < d->S; ++k) {
     if (d->h[k] != (d->H >> k) || d->w[k] != (d->W >> k)) return COLVO_E_BAD_DESC;
@@ -80,6 +80,7 @@ size_t carve_fwd(const ColvoDesc* d, void* ws, FwdBuffers& F) {
   F.smooth_part = c.take<double>(BS * kSmoothMaxChunks * 3);
   F.loss_part = c.take<double>((size_t)d->B * tiles);
   F.g_part = c.take<double>((size_t)d->B * tiles * d->N * kMaxS * 2);
+  F.iw = c.take<float>(BNS * 3 * (size_t)d->H * d->W);
   F.pyr[0] = nullptr;
   for (int k = 1; k < kMaxS; ++k) F.pyr[k] = (k < d->S) ? c.take<float>((size_t)d->B * 3 * d->h[k] * d->w[k]) : nullptr;
   return c.off;
@@ -111,6 +112,8 @@ size_t carve_saved(const ColvoDesc* d, double* saved, SavedView& sv) {
       sv.s_field[k] = nullptr;
     }
   }
+  sv.coef = f ? f + nf : nullptr;
+  nf += (size_t)d->B * d->S * 9 * d->H * d->W;
   return nd + (nf + 1) / 2;
 }
 

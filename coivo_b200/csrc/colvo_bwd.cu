@@ -3,39 +3,32 @@
 // saves only sel, (a, b), the LCC statistics, dL/da, dL/db and the smoothness adjoint field;
 // everything else is recomputed.
 //
-//   k_photo_bwd      per 32x8 tile (+2 px halo): re-warp, SSIM adjoint in gather form, LCC
-//                    adjoint, bilinear scatter-add (REDG) into grad_srcs, projection adjoint
-//                    -> full-resolution depth adjoint + per-tile pose-gradient partials;
-//                    scale 0 also receives its smoothness gradient here
+//   k_photo_bwd      per 32x8 tile: re-warp of the own pixel, SSIM adjoint gathered from the
+//                    coefficient fields the forward saved, LCC adjoint, bilinear scatter-add
+//                    (REDG) into grad_srcs, projection adjoint -> full-resolution depth adjoint
+//                    + per-tile pose-gradient partials; scale 0 also gets its smoothness gradient
 //   k_depth_gather   adjoint of the bilinear depth up-sample in gather form (no atomics),
 //                    plus the smoothness gradient of scales k >= 1
 //   k_pose_final     deterministic reduction of the pose-gradient partials
 #include "colvo_kernels.cuh"
 
+#ifndef COLVO_MINB_BWD      // CTAs per SM the register allocator must allow -- tuned on B200, see DESIGN.md
+#define COLVO_MINB_BWD 3
+#endif
+
 namespace colvo {
 
-constexpr int kBH = kTileH + 4, kBW = kTileW + 4;   // tile + 2-pixel halo (raw warped image)
-constexpr int kBN = kBH * kBW;
 constexpr int kCH = kTileH + 2, kCW = kTileW + 2;   // tile + 1-pixel halo (window centres)
 constexpr int kCN = kCH * kCW;
-constexpr int kRing = 4 * kBW + 4 * kTileH;         // halo positions of the kBH x kBW tile
 
-__device__ __forceinline__ void ring_pos(int j, int& r, int& c) {
-  if (j < 2 * kBW) {
-    r = j / kBW;
-    c = j - r * kBW;
-  } else if (j < 4 * kBW) {
-    j -= 2 * kBW;
-    int rr = j / kBW;
-    r = kTileH + 2 + rr;
-    c = j - rr * kBW;
-  } else {
-    j -= 4 * kBW;
-    r = 2 + (j >> 2);
-    int cc = j & 3;
-    c = (cc < 2) ? cc : (kTileW + cc);
-  }
+// 4-byte asynchronous global->shared copy (LDGSTS); zero-fills the destination when !pred
+__device__ __forceinline__ void cp_async4(float* smem, const float* gmem, bool pred) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  const int sz = pred ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(sa), "l"(gmem), "r"(sz));
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 // smoothness gradient of one depth texel from the saved adjoint field (grad_loss folded in by the caller)
 __device__ __forceinline__ float smooth_grad(float s, float D, float inv, float corr) {
@@ -43,40 +36,40 @@ __device__ __forceinline__ float smooth_grad(float s, float D, float inv, float 
   return -(s * inv - corr) * dr * dr;
 }
 
+// One CTA = one 32x8 tile of one triplet.  The SSIM adjoint coefficients of every window were
+// written by the forward (for the winning candidate), so the tile needs no halo re-warp: per scale
+// the CTA stages the coefficient tile (+1 halo) in shared memory, then every thread warps its own
+// pixel once per source, gathers the 3x3 neighbourhood of coefficients, and pushes the result
+// through the LCC, bilinear and projection adjoints.
 template <int NS>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, COLVO_MINB_BWD)
     k_photo_bwd(KP P, const float* __restrict__ grad_loss, const uint8_t* __restrict__ sel,
                 const double* __restrict__ saved_frame, const double* __restrict__ saved_scale,
-                const float* __restrict__ s_field0, float* __restrict__ grad_d0, float* __restrict__ dD1,
-                float* __restrict__ dD2, float* __restrict__ dD3, float* __restrict__ grad_srcs,
-                double* __restrict__ pose_part) {
-  __shared__ float xs[3 * kBN];
-  __shared__ float ys[3 * kBN];
-  __shared__ float ymu[3 * kCN];
-  __shared__ float ysg[3 * kCN];
-  __shared__ float4 coef[kCN * 3];                  // per window centre and channel: (ca, cb, cg, -)
-  __shared__ unsigned char sels[kMaxS][kCN];
-  __shared__ float cst[NS][kMaxS][6];               // a, b, P, Q, mean_x, mean_y per warped frame
-  __shared__ float cst_sm[2];                       // scale 0: 1/(mean+eps), sum(s d)/(n (mean+eps)^2)
-  __shared__ double red[(kThreads / 32) * NS * 12];
+                const float* __restrict__ s_field0, const float* __restrict__ coef_in, float* __restrict__ grad_d0,
+                float* __restrict__ dD1, float* __restrict__ dD2, float* __restrict__ dD3,
+                float* __restrict__ grad_srcs, double* __restrict__ pose_part) {
+  // dynamic shared memory, carved by hand
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4 (*coef)[kCN * 3] = reinterpret_cast<float4 (*)[kCN * 3]>(smem_raw);   // [2]: (ca, cb, cg, -) per window
+                                                                               // centre and channel, double-buffered over k
+  double* red = reinterpret_cast<double*>(smem_raw + sizeof(float4) * 2 * kCN * 3);
+  float (*cst)[kMaxS][6] = reinterpret_cast<float (*)[kMaxS][6]>(red + (kThreads / 32) * NS * 12);
+                                                    // [NS]: a, b, P, Q, mean_x, mean_y per warped frame
+  float* cst_sm = reinterpret_cast<float*>(cst + NS);   // scale 0: 1/(mean+eps), sum(s d)/(n (mean+eps)^2)
+  unsigned char (*sels)[kCN] = reinterpret_cast<unsigned char (*)[kCN]>(cst_sm + 2);   // [kMaxS]
 
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
   const int b = blockIdx.z, x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
   const int px = x0 + tx, py = y0 + ty;
   const bool in_img = (px < P.W) && (py < P.H);
-  const int qx = reflect_clamp(px, P.W), qy = reflect_clamp(py, P.H);   // addressable stand-in when outside
+  const int qx = imin(px, P.W - 1), qy = imin(py, P.H - 1);             // addressable stand-in when outside
+  const int qo = qy * P.W + qx;
   const float* tg = P.tgt + (long long)b * P.tgt_bs;
   const Cam cam = load_cam(P, b);
   const float go = __ldg(grad_loss);
   const float wscale = go / ((float)P.S * (float)P.B * (float)P.HW);
 
-  // ---- phase 0: target tile (+2), selection masks (+1), per-frame constants ----
-  for (int idx = tid; idx < kBN; idx += kThreads) {
-    int r = idx / kBW, c = idx - r * kBW;
-    int gy = reflect_clamp(y0 - 2 + r, P.H), gx = reflect_clamp(x0 - 2 + c, P.W);
-#pragma unroll
-    for (int ch = 0; ch < 3; ++ch) ys[ch * kBN + idx] = __ldg(tg + (ch * P.HW + gy * P.W + gx));
-  }
+  // ---- phase 0: selection masks (+1 halo), per-frame constants ----
   for (int idx = tid; idx < kCN; idx += kThreads) {
     int r = idx / kCW, c = idx - r * kCW;
     int gy = y0 - 1 + r, gx = x0 - 1 + c;
@@ -106,132 +99,96 @@ __global__ void __launch_bounds__(kThreads, 2)
     cst_sm[0] = (float)(1.0 / me);
     cst_sm[1] = (float)(sc[1] / ((double)P.HW * me * me));
   }
-  __syncthreads();
-  for (int idx = tid; idx < kCN; idx += kThreads) {
-    int r = idx / kCW, c = idx - r * kCW;
-#pragma unroll
-    for (int ch = 0; ch < 3; ++ch) {
-      float s = 0.f, ss = 0.f;
-#pragma unroll
-      for (int j = 0; j < 9; ++j) {
-        float v = ys[ch * kBN + (r + j / 3) * kBW + c + j % 3];
-        s += v;
-        ss = fmaf(v, v, ss);
-      }
-      float m = s * (1.0f / 9.0f);
-      ymu[ch * kCN + idx] = m;
-      ysg[ch * kCN + idx] = ss * (1.0f / 9.0f) - m * m;
-    }
-  }
-  // (the first __syncthreads of the (k, n) loop orders these writes before their readers)
 
-  // reflect-padding multiplicities of the 3x3 gather at the own pixel, as one 9-entry product table
-  float m9[9];
+  // reflect-padding multiplicities of the 3x3 gather at the own pixel (per axis)
+  float my3[3], mx3[3];
 #pragma unroll
-  for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-    for (int dx = 0; dx < 3; ++dx)
-      m9[3 * dy + dx] = reflect_mult(py, py + dy - 1, P.H) * reflect_mult(px, px + dx - 1, P.W);
+  for (int d = 0; d < 3; ++d) {
+    my3[d] = reflect_mult(py, py + d - 1, P.H);
+    mx3[d] = reflect_mult(px, px + d - 1, P.W);
+  }
   float yq[3];
 #pragma unroll
-  for (int ch = 0; ch < 3; ++ch) yq[ch] = ys[ch * kBN + (ty + 2) * kBW + tx + 2];
-
-  // positions this thread warps for every frame: its own pixel and (tid < kRing) one halo position
+  for (int ch = 0; ch < 3; ++ch) yq[ch] = __ldg(tg + (ch * P.HW + qo));
   const float own_rx = ray_x(qx, cam), own_ry = ray_y(qy, cam);
-  const int own_o = (ty + 2) * kBW + tx + 2;
-  int ring_o = 0, ring_gx = 0, ring_gy = 0;
-  bool ring_on = false;
-  float ring_rx = 0.f, ring_ry = 0.f;
-  if (tid < kRing) {
-    int r, c;
-    ring_pos(tid, r, c);
-    const int ry = y0 - 2 + r, rx = x0 - 2 + c;
-    ring_on = ry <= P.H && rx <= P.W;               // windows of in-image centres reach at most index n
-    ring_gx = reflect_clamp(rx, P.W);
-    ring_gy = reflect_clamp(ry, P.H);
-    ring_o = r * kBW + c;
-    ring_rx = ray_x(ring_gx, cam);
-    ring_ry = ray_y(ring_gy, cam);
-  }
+  const int oc = ty * kCW + tx;
 
-  float gp[NS][12];
+  // pose gradient: per source only sum dXp_i * D and sum dXp_i are carried (see project_adjoint)
+  float pw[NS][3], pt[NS][3];
 #pragma unroll
   for (int n = 0; n < NS; ++n)
 #pragma unroll
-    for (int j = 0; j < 12; ++j) gp[n][j] = 0.f;
+    for (int i = 0; i < 3; ++i) pw[n][i] = pt[n][i] = 0.f;
+  __syncthreads();                                   // sels, cst visible
+
+  // Coefficient tile of scale k (+1 halo; zeros where no re-projection won or outside the image), fetched with
+  // cp.async one scale ahead so its global latency hides behind the previous scale's arithmetic.
+  auto stage_coef = [&](int k) {
+    float* cbf = reinterpret_cast<float*>(coef[k & 1]);
+    const float* cin = coef_in + ((long long)(b * P.S + k) * 9) * P.HW;
+    for (int idx = tid; idx < kCN; idx += kThreads) {
+      const int r = idx / kCW, c = idx - r * kCW;
+      const unsigned char sv = sels[k][idx];
+      const bool on = sv != 255 && sv >= NS;
+      const float* p = on ? cin + (y0 - 1 + r) * P.W + (x0 - 1 + c) : cin;
+#pragma unroll
+      for (int f = 0; f < 9; ++f) cp_async4(cbf + (idx * 3 + f / 3) * 4 + f % 3, p + f * P.HW, on);
+    }
+    cp_async_commit();
+  };
+  stage_coef(0);
 
 #pragma unroll 1
   for (int k = 0; k < P.S; ++k) {
+    const float4* cb = coef[k & 1];
     const float* Dk = P.depth[k] + (long long)b * P.depth_bs[k];
     const float D_own = depth_at(P, Dk, k, qx, qy);
-    const float D_ring = ring_on ? depth_at(P, Dk, k, ring_gx, ring_gy) : 1.0f;
+    cp_async_wait_all();
+    __syncthreads();   // scale k landed for every thread, and everyone is done reading the other buffer
+    if (k + 1 < P.S) stage_coef(k + 1);
     float dD = 0.f;
+    // gather once per scale: every window centre has at most one winning source, so its coefficients go to
+    // that source's accumulators (one pass over the 3x3 neighbourhood serves both sources)
+    float A[NS][3], Bc[NS][3], G[NS][3];
 #pragma unroll
-    for (int n = 0; n < NS; ++n) {
-      const float* src = P.srcs + (long long)b * P.src_bs + (long long)n * P.src_ns;
-      const Pose pose = load_pose(P, b, n);
-      const float a = cst[n][k][0], bb = cst[n][k][1];
-      // ---- stage A: raw warped image on the tile + 2 halo; own pixel kept in registers ----
-      Geo g; Taps t; Texels tx4; float xq[3];
-      warp_sample(P, src, cam, pose, own_rx, own_ry, D_own, g, t, tx4, xq);
-      xs[own_o] = xq[0];
-      xs[kBN + own_o] = xq[1];
-      xs[2 * kBN + own_o] = xq[2];
-      if (ring_on) {
-        Geo g2; Taps t2; Texels tx2; float x2[3];
-        warp_sample(P, src, cam, pose, ring_rx, ring_ry, D_ring, g2, t2, tx2, x2);
-        xs[ring_o] = x2[0];
-        xs[kBN + ring_o] = x2[1];
-        xs[2 * kBN + ring_o] = x2[2];
-      }
-      __syncthreads();
-      // ---- stage B: SSIM adjoint coefficient fields at the window centres (tile + 1) ----
-      for (int idx = tid; idx < kCN; idx += kThreads) {
-        const int r = idx / kCW, c = idx - r * kCW;
-        const bool on = sels[k][idx] == (unsigned char)(NS + n);
-        if (on) {
-          const int o = r * kBW + c;
+    for (int n = 0; n < NS; ++n)
 #pragma unroll
-          for (int ch = 0; ch < 3; ++ch) {
-            float s = 0.f, sxx = 0.f, sxy = 0.f;
+      for (int ch = 0; ch < 3; ++ch) A[n][ch] = Bc[n][ch] = G[n][ch] = 0.f;
+    if (in_img) {
 #pragma unroll
-            for (int j = 0; j < 9; ++j) {
-              const int oo = ch * kBN + o + (j / 3) * kBW + (j % 3);
-              float v = xs[oo];
-              s += v;
-              sxx = fmaf(v, v, sxx);
-              sxy = fmaf(v, ys[oo], sxy);
-            }
-            const float i9 = 1.0f / 9.0f;
-            Coef q = ssim_coef(s * i9, sxx * i9, sxy * i9, ymu[ch * kCN + idx], ysg[ch * kCN + idx], a, bb, P.alpha,
-                               P.c1, P.c2, wscale);
-            coef[idx * 3 + ch] = make_float4(q.ca, q.cb, q.cg, 0.f);
+      for (int j = 0; j < 9; ++j) {
+        const int o = oc + (j / 3) * kCW + (j % 3);
+        const unsigned char sv = sels[k][o];
+        const float m = my3[j / 3] * mx3[j % 3];
+        float mn[NS];
+#pragma unroll
+        for (int n = 0; n < NS; ++n) mn[n] = (sv == (unsigned char)(NS + n)) ? m : 0.f;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+          const float4 q = cb[o * 3 + ch];
+#pragma unroll
+          for (int n = 0; n < NS; ++n) {
+            A[n][ch] = fmaf(mn[n], q.x, A[n][ch]);
+            Bc[n][ch] = fmaf(mn[n], q.y, Bc[n][ch]);
+            G[n][ch] = fmaf(mn[n], q.z, G[n][ch]);
           }
-        } else {
-          const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-          coef[idx * 3 + 0] = z;
-          coef[idx * 3 + 1] = z;
-          coef[idx * 3 + 2] = z;
         }
       }
-      __syncthreads();
-      // ---- stage C: gather, LCC adjoint, bilinear adjoint, projection adjoint ----
+    }
+#pragma unroll
+    for (int n = 0; n < NS; ++n) {
       if (in_img) {
+        const float* src = P.srcs + (long long)b * P.src_bs + (long long)n * P.src_ns;
+        const Pose pose = load_pose(P, b, n);
+        const float a = cst[n][k][0], bb = cst[n][k][1];
         const float Pc = cst[n][k][2], Qc = cst[n][k][3], mx = cst[n][k][4], my = cst[n][k][5];
-        const int oc = ty * kCW + tx;
+        Geo g; Taps t; Texels tx4; float xq[3];
+        warp_sample(P, src, cam, pose, own_rx, own_ry, D_own, g, t, tx4, xq);
         const float wq = (sels[k][oc + kCW + 1] == (unsigned char)(NS + n)) ? wscale * (1.f - P.alpha) * (1.0f / 3.0f) : 0.f;
         float hq[3];
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
-          float A = 0.f, Bc = 0.f, G = 0.f;
-#pragma unroll
-          for (int j = 0; j < 9; ++j) {
-            const float4 q = coef[(oc + (j / 3) * kCW + (j % 3)) * 3 + ch];
-            A = fmaf(m9[j], q.x, A);
-            Bc = fmaf(m9[j], q.y, Bc);
-            G = fmaf(m9[j], q.z, G);
-          }
-          float gq = A + xq[ch] * Bc + yq[ch] * G + wq * a * sgn(fmaf(a, xq[ch], bb) - yq[ch]);
+          float gq = wscale * (A[n][ch] + xq[ch] * Bc[n][ch] + yq[ch] * G[n][ch]) + wq * a * sgn(fmaf(a, xq[ch], bb) - yq[ch]);
           float lcc = g.valid ? (Pc * ((yq[ch] - my) - 2.f * a * (xq[ch] - mx)) - Qc) : 0.f;
           hq[ch] = gq + lcc;
         }
@@ -254,7 +211,13 @@ __global__ void __launch_bounds__(kThreads, 2)
         }
         if (!t.gx) du = 0.f;
         if (!t.gy) dv = 0.f;
-        dD += project_adjoint(g, cam, pose, du, dv, gp[n]);
+        float dXp[3];
+        dD += project_adjoint(g, cam, pose, du, dv, dXp);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          pw[n][i] = fmaf(dXp[i], D_own, pw[n][i]);
+          pt[n][i] += dXp[i];
+        }
       }
     }
     if (in_img) {
@@ -273,12 +236,15 @@ __global__ void __launch_bounds__(kThreads, 2)
   const int blk = (b * P.tiles_y + blockIdx.y) * P.tiles_x + blockIdx.x;
   const int lane = tid & 31, wid = tid >> 5;
 #pragma unroll
-  for (int n = 0; n < NS; ++n)
+  for (int n = 0; n < NS; ++n) {
+    float gp[12];
+    pose_grad_expand(pw[n], pt[n], own_rx, own_ry, gp);
 #pragma unroll
     for (int j = 0; j < 12; ++j) {
-      double s = warp_sum((double)gp[n][j]);
+      double s = warp_sum(in_img ? (double)gp[j] : 0.0);
       if (lane == 0) red[wid * (NS * 12) + n * 12 + j] = s;
     }
+  }
   __syncthreads();
   if (tid < NS * 12) {
     double s = 0.0;
@@ -368,6 +334,12 @@ __global__ void __launch_bounds__(kThreads)
 // ------------------------------------------------------------------------------------------
 static inline int div_up(int a, int b) { return (a + b - 1) / b; }
 
+template <int NS>
+static size_t photo_bwd_smem() {
+  return sizeof(float4) * 2 * kCN * 3 + sizeof(double) * (kThreads / 32) * NS * 12 +
+         sizeof(float) * NS * kMaxS * 6 + sizeof(float) * 2 + kMaxS * kCN;
+}
+
 cudaError_t launch_backward(const KP& P, const BwdBuffers& Wk, const float* grad_loss, const uint8_t* sel,
                             const SavedView& sv, float* const* grad_depth, float* grad_T, float* grad_srcs,
                             cudaStream_t st) {
@@ -379,11 +351,14 @@ cudaError_t launch_backward(const KP& P, const BwdBuffers& Wk, const float* grad
   dim3 grid(P.tiles_x, P.tiles_y, P.B);
   {
     ScopedKernelTimer tm(2, st);
+    // opting in to > 48 KB of dynamic shared memory is a per-function, per-device attribute: cheap and idempotent
+    cudaFuncSetAttribute(k_photo_bwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)photo_bwd_smem<1>());
+    cudaFuncSetAttribute(k_photo_bwd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)photo_bwd_smem<2>());
     if (P.N == 1)
-      k_photo_bwd<1><<<grid, kThreads, 0, st>>>(P, grad_loss, sel, sv.frame, sv.scale, sv.s_field[0], grad_depth[0],
+      k_photo_bwd<1><<<grid, kThreads, photo_bwd_smem<1>(), st>>>(P, grad_loss, sel, sv.frame, sv.scale, sv.s_field[0], sv.coef, grad_depth[0],
                                                 Wk.dDhat[1], Wk.dDhat[2], Wk.dDhat[3], grad_srcs, Wk.pose_part);
     else
-      k_photo_bwd<2><<<grid, kThreads, 0, st>>>(P, grad_loss, sel, sv.frame, sv.scale, sv.s_field[0], grad_depth[0],
+      k_photo_bwd<2><<<grid, kThreads, photo_bwd_smem<2>(), st>>>(P, grad_loss, sel, sv.frame, sv.scale, sv.s_field[0], sv.coef, grad_depth[0],
                                                 Wk.dDhat[1], Wk.dDhat[2], Wk.dDhat[3], grad_srcs, Wk.pose_part);
   }
   k_pose_final<<<P.B * P.N, kThreads, 0, st>>>(P, Wk.pose_part, grad_T);

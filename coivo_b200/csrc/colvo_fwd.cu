@@ -10,6 +10,17 @@
 //   k_finalize_fwd  deterministic final sums -> loss, G_a, G_b, sum s*d               (row 10)
 #include "colvo_kernels.cuh"
 
+// occupancy knobs (CTAs per SM the register allocator must allow) -- tuned on B200, see DESIGN.md
+#ifndef COLVO_MINB_FWD
+#define COLVO_MINB_FWD 3
+#endif
+#ifndef COLVO_MINB_STATS
+#define COLVO_MINB_STATS 4
+#endif
+#ifndef COLVO_Y_REGS        // 1: keep the 3x3 target window of the own pixel in registers (27 regs)
+#define COLVO_Y_REGS 0
+#endif
+
 namespace colvo {
 
 static inline int div_up(int a, int b) { return (a + b - 1) / b; }
@@ -70,10 +81,12 @@ __global__ void __launch_bounds__(kThreads)
 
 // ------------------------------------------------------------------------------------------
 // One CTA = one (b, k) and a chunk of pixels; both sources are warped by the same thread so the
-// ray, the up-sampled depth and the target pixel are loaded once.
+// ray, the up-sampled depth and the target pixel are loaded once.  The raw warped frames are also
+// written out ([B,N,S,3,H,W] scratch): the tile kernel needs them with a halo, and re-warping there
+// costs more issue slots than the 12 B/pixel round trip costs bandwidth on this ALU-bound path.
 template <int NS>
-__global__ void __launch_bounds__(kThreads)
-    k_warp_stats(KP P, double* __restrict__ part, uint8_t* __restrict__ valid_out) {
+__global__ void __launch_bounds__(kThreads, COLVO_MINB_STATS)
+    k_warp_stats(KP P, double* __restrict__ part, uint8_t* __restrict__ valid_out, float* __restrict__ iw_out) {
   __shared__ double sm[(kThreads / 32) * 5 * NS];
   const int bk = blockIdx.y, k = bk % P.S, b = bk / P.S;
   const Cam cam = load_cam(P, b);
@@ -100,6 +113,12 @@ __global__ void __launch_bounds__(kThreads)
         warp_sample(P, src, cam, pose[n], rx, ry, D, g, t, tx, x);
         const int bnk = (b * P.N + n) * P.S + k;
         if (valid_out) valid_out[(long long)bnk * P.HW + pix] = g.valid ? 1 : 0;
+        if (iw_out) {          // raw warped frame, re-used by k_photo_fwd instead of warping again (+halo)
+          float* o = iw_out + (long long)bnk * 3 * P.HW + pix;
+          o[0] = x[0];
+          o[P.HW] = x[1];
+          o[2 * (long long)P.HW] = x[2];
+        }
         if (g.valid) {
           acc[5 * n + 0] += 3.0;
           acc[5 * n + 1] += (double)(x[0] + x[1] + x[2]);
@@ -167,37 +186,78 @@ __global__ void __launch_bounds__(32)
 
 // ------------------------------------------------------------------------------------------
 // The fused tile kernel.  One CTA = one 32x8 output tile of one triplet; the (k, n) loops run
-// inside the CTA so the target tile, its SSIM moments, the identity candidates and the pixel
-// rays are computed once and shared by all 2*S warps.  The warped tile is double-buffered in
-// shared memory: one __syncthreads per warped frame.
+// inside the CTA so the target tile, its SSIM moments and the identity candidates are computed
+// once and shared by all 2*S warped frames.  The warped tile (+1 halo, read from the frames
+// k_warp_stats left in scratch) is double-buffered in shared memory: one __syncthreads per frame.
 constexpr int kFH = kTileH + 2, kFW = kTileW + 2;   // tile + 1-pixel SSIM halo
 constexpr int kFN = kFH * kFW;
 
-__device__ __forceinline__ float pe_own(const float* __restrict__ xb /* [3][kFN] */, const float (&y9)[3][9],
-                                        const float (&muy)[3], const float (&sgy)[3], int o /* ty*kFW+tx */, float a,
-                                        float b, const KP& P, float* dpa, float* dpb) {
+// The 3x3 target window of the own pixel: either 27 registers or re-read from the target tile.
+struct YWin {
+#if COLVO_Y_REGS
+  float v[3][9];
+#endif
+  const float* ys;      // [3][kFN] target tile in shared memory
+  int o;                // ty*kFW + tx
+  float mu[3], sg[3];   // window mean and variance of the target
+  __device__ __forceinline__ float at(int c, int j) const {
+#if COLVO_Y_REGS
+    return v[c][j];
+#else
+    return ys[c * kFN + o + (j / 3) * kFW + (j % 3)];
+#endif
+  }
+};
+
+__device__ __forceinline__ float pe_own(const float* __restrict__ xb /* [3][kFN] */, const YWin& y, float a, float b,
+                                        const KP& P, float* dpa, float* dpb, bool want_cf, Coef (&cf)[3]) {
   float pe = 0.f;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    float s = 0.f, sxx = 0.f, sxy = 0.f, xc = 0.f;
+    float s = 0.f, sxx = 0.f, sxy = 0.f, xc = 0.f, yc = 0.f;
 #pragma unroll
     for (int j = 0; j < 9; ++j) {
-      float v = xb[c * kFN + o + (j / 3) * kFW + (j % 3)];
-      if (j == 4) xc = v;
+      const float v = xb[c * kFN + y.o + (j / 3) * kFW + (j % 3)];
+      const float w = y.at(c, j);
+      if (j == 4) { xc = v; yc = w; }
       s += v;
       sxx = fmaf(v, v, sxx);
-      sxy = fmaf(v, y9[c][j], sxy);
+      sxy = fmaf(v, w, sxy);
     }
     const float i9 = 1.0f / 9.0f;
-    pe += pe_channel(s * i9, sxx * i9, sxy * i9, muy[c], sgy[c], xc, y9[c][4], a, b, P.alpha, P.c1, P.c2, dpa, dpb);
+    pe += pe_channel(s * i9, sxx * i9, sxy * i9, y.mu[c], y.sg[c], xc, yc, a, b, P.alpha, P.c1, P.c2, dpa, dpb, want_cf,
+                     cf[c]);
   }
   return pe * (1.0f / 3.0f);
 }
+__device__ __forceinline__ float pe_own(const float* __restrict__ xb, const YWin& y, float a, float b, const KP& P) {
+  Coef unused[3];
+  return pe_own(xb, y, a, b, P, nullptr, nullptr, false, unused);
+}
+__device__ __forceinline__ void ywin_init(YWin& y, const float* ys, int own) {
+  y.ys = ys;
+  y.o = own;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float s = 0.f, ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+      float v = ys[c * kFN + own + (j / 3) * kFW + (j % 3)];
+#if COLVO_Y_REGS
+      y.v[c][j] = v;
+#endif
+      s += v;
+      ss = fmaf(v, v, ss);
+    }
+    y.mu[c] = s * (1.0f / 9.0f);
+    y.sg[c] = ss * (1.0f / 9.0f) - y.mu[c] * y.mu[c];
+  }
+}
 
 template <int NS>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, COLVO_MINB_FWD)
     k_photo_fwd(KP P, const float* __restrict__ ab, uint8_t* __restrict__ sel_out, double* __restrict__ loss_part,
-                double* __restrict__ g_part, int need_g) {
+                double* __restrict__ g_part, int need_g, float* __restrict__ coef_out, const float* __restrict__ iw) {
   constexpr int NV = 1 + NS * kMaxS * 2;
   __shared__ float ys[3 * kFN];
   __shared__ float xs[2][3 * kFN];
@@ -209,25 +269,17 @@ __global__ void __launch_bounds__(kThreads, 2)
   const bool in_img = (px < P.W) && (py < P.H);
   const int own = ty * kFW + tx;
   const float* tg = P.tgt + (long long)b * P.tgt_bs;
-  const Cam cam = load_cam(P, b);
 
-  // the (at most) two halo-tile positions this thread fills for every warped frame
-  int pso[2], pgo[2], pgx[2], pgy[2];
-  bool pok[2], pneed[2];
-  float prx[2], pry[2];
+  // the (at most) two halo-tile positions this thread fills for every frame (reflect-padded coordinates)
+  int pso[2], pgo[2];
+  bool pok[2];
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
     const int idx = tid + j * kThreads;
     pok[j] = idx < kFN;
     const int r = idx / kFW, c = idx - r * kFW;
-    const int ry = y0 - 1 + r, rx = x0 - 1 + c;
-    pneed[j] = pok[j] && ry <= P.H && rx <= P.W;      // positions further out are never read
-    pgy[j] = reflect_clamp(ry, P.H);
-    pgx[j] = reflect_clamp(rx, P.W);
     pso[j] = idx;
-    pgo[j] = pgy[j] * P.W + pgx[j];
-    prx[j] = ray_x(pgx[j], cam);
-    pry[j] = ray_y(pgy[j], cam);
+    pgo[j] = reflect_clamp(y0 - 1 + r, P.H) * P.W + reflect_clamp(x0 - 1 + c, P.W);
   }
 #pragma unroll
   for (int j = 0; j < 2; ++j)
@@ -237,20 +289,8 @@ __global__ void __launch_bounds__(kThreads, 2)
     }
   __syncthreads();
 
-  float y9[3][9], muy[3], sgy[3];
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    float s = 0.f, ss = 0.f;
-#pragma unroll
-    for (int j = 0; j < 9; ++j) {
-      float v = ys[c * kFN + own + (j / 3) * kFW + (j % 3)];
-      y9[c][j] = v;
-      s += v;
-      ss = fmaf(v, v, ss);
-    }
-    muy[c] = s * (1.0f / 9.0f);
-    sgy[c] = ss * (1.0f / 9.0f) - muy[c] * muy[c];
-  }
+  YWin yw;
+  ywin_init(yw, ys, own);
 
   // identity candidates: raw sources, no calibration (oracle A10)
   float ident[NS];
@@ -265,12 +305,12 @@ __global__ void __launch_bounds__(kThreads, 2)
         for (int ch = 0; ch < 3; ++ch) xb[ch * kFN + pso[j]] = __ldg(src + (ch * P.HW + pgo[j]));
       }
     __syncthreads();
-    ident[n] = in_img ? pe_own(xb, y9, muy, sgy, own, 1.0f, 0.0f, P, nullptr, nullptr) : 0.f;
+    ident[n] = in_img ? pe_own(xb, yw, 1.0f, 0.0f, P) : 0.f;
   }
 
-  float acc[NV];
-#pragma unroll
-  for (int i = 0; i < NV; ++i) acc[i] = 0.f;
+  float loss_acc = 0.f;
+  const int lane = tid & 31, wid = tid >> 5;
+  for (int i = tid; i < (kThreads / 32) * NV; i += kThreads) red[i] = 0.0;   // slots of unused scales stay 0
 
 #pragma unroll
   for (int k = 0; k < kMaxS; ++k) {
@@ -281,58 +321,68 @@ __global__ void __launch_bounds__(kThreads, 2)
       for (int n = 1; n < NS; ++n)
         if (ident[n] < best) { best = ident[n]; sel = n; }
       float dpa[NS], dpb[NS];
-      const float* Dk = P.depth[k] + (long long)b * P.depth_bs[k];
-      float Dh[2];
-#pragma unroll
-      for (int j = 0; j < 2; ++j) Dh[j] = pneed[j] ? depth_at(P, Dk, k, pgx[j], pgy[j]) : 1.0f;
+      Coef cf[NS][3];          // unit-weight SSIM adjoint coefficients of candidate n, until the winner is known
 #pragma unroll
       for (int n = 0; n < NS; ++n) {
-        const float* src = P.srcs + (long long)b * P.src_bs + (long long)n * P.src_ns;
-        const Pose pose = load_pose(P, b, n);
         const int bnk = (b * P.N + n) * P.S + k;
         const float a = __ldg(ab + 2 * bnk), bb = __ldg(ab + 2 * bnk + 1);
+        const float* wsrc = iw + (long long)bnk * 3 * P.HW;
         float* xb = xs[(NS + k * NS + n) & 1];
 #pragma unroll
         for (int j = 0; j < 2; ++j)
-          if (pneed[j]) {
-            Geo g; Taps t; Texels tx4; float x[3];
-            warp_sample(P, src, cam, pose, prx[j], pry[j], Dh[j], g, t, tx4, x);
-            xb[pso[j]] = x[0];
-            xb[kFN + pso[j]] = x[1];
-            xb[2 * kFN + pso[j]] = x[2];
+          if (pok[j]) {
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) xb[ch * kFN + pso[j]] = __ldg(wsrc + (ch * P.HW + pgo[j]));
           }
         __syncthreads();
         dpa[n] = 0.f;
         dpb[n] = 0.f;
         if (in_img) {
-          float pe = pe_own(xb, y9, muy, sgy, own, a, bb, P, need_g ? &dpa[n] : nullptr, need_g ? &dpb[n] : nullptr);
+          float pe = pe_own(xb, yw, a, bb, P, need_g ? &dpa[n] : nullptr, need_g ? &dpb[n] : nullptr,
+                            coef_out != nullptr, cf[n]);
           if (pe < best) { best = pe; sel = NS + n; }
         }
       }
       if (in_img) {
-        acc[0] += best;
+        loss_acc += best;
         if (sel_out) sel_out[((long long)b * P.S + k) * P.HW + py * P.W + px] = (uint8_t)sel;
 #pragma unroll
         for (int n = 0; n < NS; ++n) {
           if (sel == NS + n) {
-            acc[1 + (n * kMaxS + k) * 2 + 0] += dpa[n] * (1.0f / 3.0f);
-            acc[1 + (n * kMaxS + k) * 2 + 1] += dpb[n] * (1.0f / 3.0f);
+            if (coef_out) {     // the backward reads these only where sel says a re-projection won
+              float* co = coef_out + ((long long)(b * P.S + k) * 9) * P.HW + py * P.W + px;
+#pragma unroll
+              for (int ch = 0; ch < 3; ++ch) {
+                co[(3 * ch + 0) * (long long)P.HW] = cf[n][ch].ca;
+                co[(3 * ch + 1) * (long long)P.HW] = cf[n][ch].cb;
+                co[(3 * ch + 2) * (long long)P.HW] = cf[n][ch].cg;
+              }
+            }
+          }
+        }
+      }
+      // dL/da, dL/db of this scale: sums of large terms of both signs -> reduce in fp64 right away
+      // (each slot is written exactly once per warp, so no accumulator registers are carried)
+      if (need_g) {
+#pragma unroll
+        for (int n = 0; n < NS; ++n) {
+          const bool w = in_img && sel == NS + n;
+          double sa = warp_sum(w ? (double)(dpa[n] * (1.0f / 3.0f)) : 0.0);
+          double sb = warp_sum(w ? (double)(dpb[n] * (1.0f / 3.0f)) : 0.0);
+          if (lane == 0) {
+            red[wid * NV + 1 + (n * kMaxS + k) * 2 + 0] = sa;
+            red[wid * NV + 1 + (n * kMaxS + k) * 2 + 1] = sb;
           }
         }
       }
     }
   }
 
-  // Per-tile partials.  dL/da and dL/db are sums of large terms of both signs: reduce them in
-  // fp64 (each thread contributes at most one fp32 term per slot, so nothing is lost before).
+  // Per-tile partials (thread i < NV sums the 8 per-warp values of slot i).
   const int blk = (b * P.tiles_y + blockIdx.y) * P.tiles_x + blockIdx.x;
-  const int lane = tid & 31, wid = tid >> 5;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    if (i == 0 || need_g) {
-      double s = warp_sum((double)acc[i]);
-      if (lane == 0) red[wid * NV + i] = s;
-    }
+  {
+    double s = warp_sum((double)loss_acc);
+    if (lane == 0) red[wid * NV] = s;
   }
   __syncthreads();
   if (tid < NV && (tid == 0 || need_g)) {
@@ -528,21 +578,9 @@ __global__ void __launch_bounds__(kThreads, 2)
   __syncthreads();
   double acc[2] = {0.0, 0.0};
   if (in_img && vs[own + kFW + 1]) {
-    float y9[3][9], muy[3], sgy[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      float s = 0.f, ss = 0.f;
-#pragma unroll
-      for (int j = 0; j < 9; ++j) {
-        float v = ys[c * kFN + own + (j / 3) * kFW + (j % 3)];
-        y9[c][j] = v;
-        s += v;
-        ss = fmaf(v, v, ss);
-      }
-      muy[c] = s * (1.0f / 9.0f);
-      sgy[c] = ss * (1.0f / 9.0f) - muy[c] * muy[c];
-    }
-    float pe = pe_own(xs, y9, muy, sgy, own, __ldg(ab + 2 * b), __ldg(ab + 2 * b + 1), P, nullptr, nullptr);
+    YWin yw;
+    ywin_init(yw, ys, own);
+    float pe = pe_own(xs, yw, __ldg(ab + 2 * b), __ldg(ab + 2 * b + 1), P);
     acc[0] = (double)pe;
     acc[1] = 1.0;
   }
@@ -585,20 +623,22 @@ cudaError_t launch_forward(const KP& P, const FwdBuffers& Wk, float* loss, float
   const int chunks = P.B * total_chunks(P);
   const int n_pyr = (P.S > 1) ? imin(div_up(P.B * 3 * P.h[1] * P.w[1], kThreads), 148 * 4) : 0;
   k_prepass<<<n_pyr + chunks, kThreads, 0, st>>>(P, n_pyr, Wk.pyr[1], Wk.pyr[2], Wk.pyr[3], Wk.disp_part);
-  if (lcc || valid) {
+  {
     ScopedKernelTimer tm(3, st);
     dim3 g(Wk.stat_chunks, P.B * P.S);
-    if (P.N == 1) k_warp_stats<1><<<g, kThreads, 0, st>>>(P, Wk.stat_part, valid);
-    else k_warp_stats<2><<<g, kThreads, 0, st>>>(P, Wk.stat_part, valid);
+    if (P.N == 1) k_warp_stats<1><<<g, kThreads, 0, st>>>(P, Wk.stat_part, valid, Wk.iw);
+    else k_warp_stats<2><<<g, kThreads, 0, st>>>(P, Wk.stat_part, valid, Wk.iw);
   }
   k_lcc_solve<<<BNS, 32, 0, st>>>(P, Wk.stat_part, Wk.stat_chunks, ab, save ? sv.frame : nullptr);
   dim3 grid(P.tiles_x, P.tiles_y, P.B);
   {
     ScopedKernelTimer tm(1, st);
     if (P.N == 1)
-      k_photo_fwd<1><<<grid, kThreads, 0, st>>>(P, ab, sel, Wk.loss_part, Wk.g_part, need_g);
+      k_photo_fwd<1><<<grid, kThreads, 0, st>>>(P, ab, sel, Wk.loss_part, Wk.g_part, need_g, save ? sv.coef : nullptr,
+                                                Wk.iw);
     else
-      k_photo_fwd<2><<<grid, kThreads, 0, st>>>(P, ab, sel, Wk.loss_part, Wk.g_part, need_g);
+      k_photo_fwd<2><<<grid, kThreads, 0, st>>>(P, ab, sel, Wk.loss_part, Wk.g_part, need_g, save ? sv.coef : nullptr,
+                                                Wk.iw);
   }
   if (save)
     k_smooth_fwd<true><<<chunks, kThreads, 0, st>>>(P, Wk.disp_part, Wk.pyr[1], Wk.pyr[2], Wk.pyr[3], Wk.smooth_part,
@@ -615,7 +655,7 @@ cudaError_t launch_forward(const KP& P, const FwdBuffers& Wk, float* loss, float
 
 cudaError_t launch_consistency(const KP& P, double* stat_part, int stat_chunks, double* pe_part, float* ab, float* out,
                                cudaStream_t st) {
-  k_warp_stats<1><<<dim3(stat_chunks, P.B), kThreads, 0, st>>>(P, stat_part, nullptr);
+  k_warp_stats<1><<<dim3(stat_chunks, P.B), kThreads, 0, st>>>(P, stat_part, nullptr, nullptr);
   k_lcc_solve<<<P.B, 32, 0, st>>>(P, stat_part, stat_chunks, ab, nullptr);
   k_consistency_pe<<<dim3(P.tiles_x, P.tiles_y, P.B), kThreads, 0, st>>>(P, ab, pe_part);
   k_consistency_final<<<P.B, kThreads, 0, st>>>(P, pe_part, ab, out);

@@ -19,6 +19,8 @@ constexpr int kSmoothPixPerBlock = 2048;
 // saved[] layout: doubles  [B*N*S][kSavedPerFrame]  n, mean_x, mean_y, 1/(n (var+eps)), a, b, G_a, G_b
 //                 doubles  [B*S][kSavedPerScale]    mean inverse depth, sum_p s_p d_p
 //                 floats   s-field of every scale   dL_smooth/dd*_p for grad_loss = 1, [B,h_k,w_k]
+//                 floats   [B,S,9,H,W]              SSIM adjoint coefficients (ca, cb, cg per channel) of the
+//                                                   winning re-projection candidate (undefined where identity won)
 constexpr int kSavedPerFrame = 8;
 constexpr int kSavedPerScale = 2;
 
@@ -136,6 +138,7 @@ struct FwdBuffers {
   double* smooth_part;   // [B*S][kSmoothMaxChunks][3]   sum_x, sum_y, sum s*d
   double* loss_part;     // [B*tiles]
   double* g_part;        // [B*tiles][N*kMaxS*2]
+  float* iw;             // [B,N,S,3,H,W] raw warped frames (k_warp_stats -> k_photo_fwd)
 };
 struct BwdBuffers {
   float* dDhat[kMaxS];   // k >= 1: [B,H,W] full-resolution depth adjoint before the up-sample adjoint
@@ -145,6 +148,7 @@ struct SavedView {       // the caller-owned `saved` buffer, carved
   double* frame;         // [B*N*S][kSavedPerFrame]
   double* scale;         // [B*S][kSavedPerScale]
   float* s_field[kMaxS]; // [B,h_k,w_k]
+  float* coef;           // [B,S,9,H,W] unit-weight SSIM adjoint coefficients of the winning re-projection
 };
 
 // one-shot event bracket around one kernel launch (colvo_debug_time_kernel)

@@ -162,11 +162,26 @@ CV_HD SsimParts ssim_parts(float mut, float st, float stxy, float muy, float sy,
 CV_HD float clamp01(float t) { return fminf(fmaxf(t, 0.f), 1.f); }
 CV_HD float sgn(float x) { return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f); }
 
+// coefficient fields of the SSIM adjoint in gather form (SURVEY.md appendix A, re-derived for
+// raw moments):  d pe_p / d x_q  =  ca_p + x_q * cb_p + y_q * cg_p   for every occurrence of q in
+// the reflect-padded 3x3 window of p (already includes alpha/3 * (-1/2) * 1/9 * active).
+struct Coef { float ca, cb, cg; };
+CV_HD Coef coef_from_parts(const SsimParts& q, float mu, float muy, float a, float alpha, float wp) {
+  Coef o;
+  float act = (q.t >= 0.f && q.t <= 1.f) ? wp * (-0.5f * alpha) * (1.0f / 27.0f) : 0.f;
+  float dmu = a * q.dmu, ds = a * a * q.dsx, dsxy = a * q.dsxy;
+  o.ca = act * (dmu - 2.f * mu * ds - muy * dsxy);
+  o.cb = act * 2.f * ds;
+  o.cg = act * dsxy;
+  return o;
+}
+
 // photometric error of one pixel from per-channel raw window moments and the centre sample
 //   pe = alpha * mean_c clamp((1 - SSIM_c)/2) + (1 - alpha) * mean_c |a x_c + b - y_c|
-// Optionally also d pe / d a and d pe / d b (the LCC adjoint sums G_a, G_b of the forward).
+// Optionally also d pe / d a and d pe / d b (the LCC adjoint sums G_a, G_b of the forward) and the
+// unit-weight adjoint coefficients of this window (saved by the forward for the backward).
 CV_HD float pe_channel(float mu, float exx, float exy, float muy, float sy, float xc, float yc, float a, float b,
-                       float alpha, float c1, float c2, float* dpa, float* dpb) {
+                       float alpha, float c1, float c2, float* dpa, float* dpb, bool want_cf, Coef& cf) {
   float s = exx - mu * mu;
   float sxy = exy - mu * muy;
   float mut = f_fma(a, mu, b);
@@ -181,26 +196,22 @@ CV_HD float pe_channel(float mu, float exx, float exy, float muy, float sy, floa
     *dpa += act * (q.dmu * mu + q.dsx * 2.f * a * s + q.dsxy * sxy) + sg * xc;
     *dpb += act * q.dmu + sg;
   }
+  if (want_cf) cf = coef_from_parts(q, mu, muy, a, alpha, 1.0f);
   return pe;
 }
+CV_HD float pe_channel(float mu, float exx, float exy, float muy, float sy, float xc, float yc, float a, float b,
+                       float alpha, float c1, float c2, float* dpa, float* dpb) {
+  Coef unused;
+  return pe_channel(mu, exx, exy, muy, sy, xc, yc, a, b, alpha, c1, c2, dpa, dpb, false, unused);
+}
 
-// coefficient fields of the SSIM adjoint in gather form (SURVEY.md appendix A, re-derived for
-// raw moments):  d pe_p / d x_q  =  ca_p + x_q * cb_p + y_q * cg_p   for every occurrence of q in
-// the reflect-padded 3x3 window of p (already includes alpha/3 * (-1/2) * 1/9 * active).
-struct Coef { float ca, cb, cg; };
 CV_HD Coef ssim_coef(float mu, float exx, float exy, float muy, float sy, float a, float b, float alpha, float c1, float c2,
                      float wp) {
   float s = exx - mu * mu;
   float sxy = exy - mu * muy;
   float mut = f_fma(a, mu, b);
   SsimParts q = ssim_parts(mut, a * a * s, a * sxy, muy, sy, c1, c2);
-  Coef o;
-  float act = (q.t >= 0.f && q.t <= 1.f) ? wp * (-0.5f * alpha) * (1.0f / 27.0f) : 0.f;
-  float dmu = a * q.dmu, ds = a * a * q.dsx, dsxy = a * q.dsxy;
-  o.ca = act * (dmu - 2.f * mu * ds - muy * dsxy);
-  o.cb = act * 2.f * ds;
-  o.cg = act * dsxy;
-  return o;
+  return coef_from_parts(q, mu, muy, a, alpha, wp);
 }
 
 // multiplicity of window centre p (= q + d, d in {-1,0,1}) in the gather at pixel q along one axis:
@@ -214,21 +225,29 @@ CV_HD float reflect_mult(int q, int p, int n) {
 }
 
 // ---- row 11: adjoint of projection / transform / back-projection for one pixel ----
-// in: du, dv = dL/du', dL/dv'.  out: dD = dL/dDhat; pose gradient accumulated into gp[12]
-// (gp[3*i + j] = dL/dR_ij, gp[9 + i] = dL/dt_i).
-CV_HD float project_adjoint(const Geo& g, const Cam& c, const Pose& p, float du, float dv, float* gp) {
+// in: du, dv = dL/du', dL/dv'.  out: dD = dL/dDhat and dXp[3] = dL/dX' (gradient w.r.t. the
+// transformed point).  The pose gradient follows from dXp alone:
+//   dL/dt_i = sum dXp_i,   dL/dR_ij = sum dXp_i * X_j   with X = D * (rx, ry, 1)
+// so a kernel only has to accumulate dXp_i and dXp_i * D per pixel (the ray is constant per pixel).
+CV_HD float project_adjoint(const Geo& g, const Cam& c, const Pose& p, float du, float dv, float (&dXp)[3]) {
   float dx = du * g.iz, dy = dv * g.iz;
-  float dXp = c.fx * dx;
-  float dYp = c.fy * dy;
-  float dZp = c.cx * dx + c.cy * dy - g.iz * (du * g.u + dv * g.v);
-  gp[0] += dXp * g.X; gp[1] += dXp * g.Y; gp[2] += dXp * g.Z;
-  gp[3] += dYp * g.X; gp[4] += dYp * g.Y; gp[5] += dYp * g.Z;
-  gp[6] += dZp * g.X; gp[7] += dZp * g.Y; gp[8] += dZp * g.Z;
-  gp[9] += dXp; gp[10] += dYp; gp[11] += dZp;
-  float dX = p.r[0] * dXp + p.r[3] * dYp + p.r[6] * dZp;
-  float dY = p.r[1] * dXp + p.r[4] * dYp + p.r[7] * dZp;
-  float dZ = p.r[2] * dXp + p.r[5] * dYp + p.r[8] * dZp;
+  dXp[0] = c.fx * dx;
+  dXp[1] = c.fy * dy;
+  dXp[2] = c.cx * dx + c.cy * dy - g.iz * (du * g.u + dv * g.v);
+  float dX = p.r[0] * dXp[0] + p.r[3] * dXp[1] + p.r[6] * dXp[2];
+  float dY = p.r[1] * dXp[0] + p.r[4] * dXp[1] + p.r[7] * dXp[2];
+  float dZ = p.r[2] * dXp[0] + p.r[5] * dXp[1] + p.r[8] * dXp[2];
   return g.rx * dX + g.ry * dY + dZ;
+}
+// expand the six per-pixel sums (w_i = sum dXp_i * D, t_i = sum dXp_i) into the 12 pose-gradient entries
+// gp[3*i + j] = dL/dR_ij, gp[9 + i] = dL/dt_i
+CV_HD void pose_grad_expand(const float (&w)[3], const float (&t)[3], float rx, float ry, float* gp) {
+  for (int i = 0; i < 3; ++i) {
+    gp[3 * i + 0] = w[i] * rx;
+    gp[3 * i + 1] = w[i] * ry;
+    gp[3 * i + 2] = w[i];
+    gp[9 + i] = t[i];
+  }
 }
 
 }  // namespace colvo

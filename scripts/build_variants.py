@@ -1,0 +1,20 @@
+"""Build tuning variants of the library into build/variants/ (occupancy knobs of the tile kernels)."""
+import os, subprocess, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from coivo_b200 import _lib
+
+VARIANTS = {
+    "f3b2": ["COLVO_MINB_FWD=3", "COLVO_MINB_BWD=2"],
+    "f3b3": ["COLVO_MINB_FWD=3", "COLVO_MINB_BWD=3"],
+    "f3b4": ["COLVO_MINB_FWD=3", "COLVO_MINB_BWD=4"],
+    "f4b3": ["COLVO_MINB_FWD=4", "COLVO_MINB_BWD=3"],
+}
+out = os.path.join(os.path.dirname(_lib.PKG_DIR), "build", "variants")
+os.makedirs(out, exist_ok=True)
+procs = []
+for name, defs in VARIANTS.items():
+    cmd = _lib.nvcc_command(os.path.join(out, f"lib_{name}.so"), defs)
+    procs.append((name, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+for name, p in procs:
+    o, _ = p.communicate()
+    print(name, "ok" if p.returncode == 0 else "FAILED\n" + o)

@@ -209,7 +209,11 @@ int harness_run(int B, int N, int S, int H, int W, unsigned flags, const float* 
             }
             if (!t.gx) du = 0;
             if (!t.gy) dv = 0;
-            dD[p] += project_adjoint(g, cam, pose, du, dv, gp);
+            float dXp[3];
+            dD[p] += project_adjoint(g, cam, pose, du, dv, dXp);
+            float wv[3] = {dXp[0] * g.Z, dXp[1] * g.Z, dXp[2] * g.Z}, tv[3] = {dXp[0], dXp[1], dXp[2]}, e[12];
+            pose_grad_expand(wv, tv, g.rx, g.ry, e);
+            for (int q = 0; q < 12; ++q) gp[q] += e[q];
           }
         float* gt = grad_T + ((size_t)b * N + n) * 16;
         for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) gt[4 * i + j] += gp[3 * i + j]; gt[4 * i + 3] += gp[9 + i]; }

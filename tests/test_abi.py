@@ -51,9 +51,12 @@ def test_workspace_and_saved_sizes():
     assert lib.colvo_workspace_bytes(ctypes.byref(d), ctypes.byref(n)) == 0
     assert lib.colvo_saved_doubles(ctypes.byref(d), ctypes.byref(m)) == 0
     assert lib.colvo_step_host_arena_bytes(ctypes.byref(d), ctypes.byref(a)) == 0
-    # doubles: 8 per warped frame + 2 per (b, k); then the fp32 smoothness adjoint fields (2 per double)
-    assert m.value == 12 * 2 * 4 * 8 + 12 * 4 * 2 + (12 * (256 * 320 + 128 * 160 + 64 * 80 + 32 * 40) + 1) // 2
-    assert 1 << 20 < n.value < 64 << 20                      # tens of MB, not the 8x I_w cache
+    # doubles: 8 per warped frame + 2 per (b, k); then fp32 (2 per double): the smoothness adjoint fields
+    # [B,h_k,w_k] and the SSIM adjoint coefficients [B,S,9,H,W]
+    nf = 12 * (256 * 320 + 128 * 160 + 64 * 80 + 32 * 40) + 12 * 4 * 9 * 256 * 320
+    assert m.value == 12 * 2 * 4 * 8 + 12 * 4 * 2 + (nf + 1) // 2
+    iw = 4 * 12 * 2 * 4 * 3 * 256 * 320                      # cached raw warped frames (stats -> tile kernel)
+    assert iw < n.value < iw + (32 << 20)
     assert a.value > n.value + 4 * 12 * (3 + 6 + 6) * 256 * 320
     assert lib.colvo_workspace_bytes(ctypes.byref(d), None) == -3
     c = ctypes.c_size_t()

@@ -119,7 +119,7 @@ def test_no_grad_and_partial_grad_paths():
     # grad_loss scaling flows through
     depth2 = [x.clone().requires_grad_() for x in args[0]]
     (3.0 * coivo_b200.photometric_loss(depth2, args[1], args[2], args[3], args[4])).backward()
-    assert torch.allclose(depth2[1].grad, 3.0 * depth[1].grad, rtol=1e-5, atol=1e-12)
+    assert relinf(depth2[1].grad, 3.0 * depth[1].grad.cpu()) < 1e-5
 
 
 def test_determinism_of_forward_and_non_scatter_grads():
