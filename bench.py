@@ -93,7 +93,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                       "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.p = None
 
@@ -131,8 +131,8 @@ def run_ours(args):
     from coivo_b200 import _lib
     from coivo_b200.synthetic import make_triplets
 
-    steps = args.steps or 50
-    warmup = args.warmup if args.warmup is not None else 10
+    steps = args.steps or 300
+    warmup = args.warmup if args.warmup is not None else 20
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -214,14 +214,17 @@ def run_ours(args):
     h_in = ([pin(x) for x in hb["depth"]], pin(hb["pose"]), pin(hb["K"]), pin(hb["tgt"]), pin(hb["srcs"]))
     for _ in range(3):
         stepper.step(*h_in)
+    stepper.finish()
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2e_steps = steps
     f0.record()
     for _ in range(e2e_steps):
         stepper.step(*h_in)
+    stepper.join()
     f1.record()
     barrier()
+    stepper.finish()
     e2e_ms = f0.elapsed_time(f1)
 
     t = torch.tensor([ms_total, e2e_ms, kern_ms], dtype=torch.float64, device=dev)
@@ -257,7 +260,7 @@ def run_ours(args):
                                   "algorithmic_bytes_per_step": B_PER_GPU * ab["step"]}},
             "e2e": {"value": world * B_PER_GPU * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": stepper.h2d_bytes(*h_in), "d2h_bytes_per_step": stepper.d2h_bytes(),
-                    "ms_per_step": e2e_ms / e2e_steps, "api": "colvo_photo_step_host (pinned host buffers, one stream)"},
+                    "ms_per_step": e2e_ms / e2e_steps, "api": f"colvo_photo_step_host (pinned host buffers; {len(stepper.spans)} batch chunks on {len(stepper.spans)} streams overlap H2D / kernels / D2H)"},
             "gpu_launches": steps * (len(_lib.KERNELS_FWD) + len(_lib.KERNELS_BWD)),
             "clocks": clocks,
         }

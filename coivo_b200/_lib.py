@@ -98,7 +98,7 @@ _SIGS = {
                                                                  _vp, _vp, ctypes.c_size_t, _vp]),
     "colvo_step_host_arena_bytes": (ctypes.c_int, [ctypes.POINTER(ColvoDesc), ctypes.POINTER(ctypes.c_size_t)]),
     "colvo_photo_step_host": (ctypes.c_int, [ctypes.POINTER(ColvoDesc), _vp, _vp, ctypes.POINTER(_vp), _vp, _vp, _vp,
-                                             ctypes.POINTER(_vp), _vp, _vp, _vp, ctypes.c_size_t, _vp]),
+                                             ctypes.POINTER(_vp), _vp, _vp, ctypes.c_float, _vp, ctypes.c_size_t, _vp]),
     "colvo_debug_time_kernel": (ctypes.c_int, [ctypes.c_int, _vp, _vp]),
 }
 EXPORTS = tuple(_SIGS)

@@ -117,7 +117,7 @@ size_t carve_saved(const ColvoDesc* d, double* saved, SavedView& sv) {
   return nd + (nf + 1) / 2;
 }
 
-__global__ void k_fill_one(float* p) { *p = 1.0f; }
+__global__ void k_fill_scalar(float* p, float v) { *p = v; }
 
 }  // namespace
 
@@ -321,7 +321,8 @@ int colvo_step_host_arena_bytes(const ColvoDesc* d, size_t* bytes) {
 
 int colvo_photo_step_host(const ColvoDesc* d_in, const float* h_tgt, const float* h_srcs, const float* const* h_depth,
                           const float* h_K, const float* h_T, float* h_loss, float* const* h_grad_depth,
-                          float* h_grad_T, float* h_grad_srcs, void* arena, size_t arena_bytes, void* stream) {
+                          float* h_grad_T, float* h_grad_srcs, float grad_scale, void* arena, size_t arena_bytes,
+                          void* stream) {
   int rc = check_desc(d_in);
   if (rc) return rc;
   if (!h_tgt || !h_srcs || !h_depth || !h_K || !h_T || !h_loss || !h_grad_depth || !h_grad_T || !arena)
@@ -349,7 +350,7 @@ int colvo_photo_step_host(const ColvoDesc* d_in, const float* h_tgt, const float
   }
   CV_COPY(A.K, h_K, B * 9, cudaMemcpyHostToDevice);
   CV_COPY(A.T, h_T, B * N * 16, cudaMemcpyHostToDevice);
-  k_fill_one<<<1, 1, 0, st>>>(A.one);
+  k_fill_scalar<<<1, 1, 0, st>>>(A.one, grad_scale);
   const float* depth_p[kMaxS] = {A.depth[0], A.depth[1], A.depth[2], A.depth[3]};
   float* gdepth_p[kMaxS] = {A.grad_depth[0], A.grad_depth[1], A.grad_depth[2], A.grad_depth[3]};
   rc = colvo_photo_forward(&d, A.tgt, A.srcs, depth_p, A.K, A.T, A.loss, A.ab, nullptr, A.sel, A.saved, A.ws,

@@ -173,49 +173,85 @@ def photometric_loss(
 
 class HostStepper:
     """End-to-end step on pinned HOST buffers through `colvo_photo_step_host`: H2D of the inputs,
-    forward, backward (grad_loss = 1), D2H of the loss and gradients, all on one stream.  This is
-    the call `bench.py` times for the `e2e` number."""
+    forward, backward, D2H of the loss and gradients.  This is the call `bench.py` times for the
+    `e2e` number.
+
+    The batch is split into `chunks` contiguous sub-batches, each on its own CUDA stream with its
+    own device arena, so the H2D copy of one chunk overlaps the kernels of another and the D2H
+    copy of a third (the three engines of the GPU work concurrently); gradients are those of the
+    whole-batch mean loss (each chunk runs with grad_loss = B_chunk / B)."""
 
     def __init__(self, B, N, S, H, W, *, device="cuda:0", lcc=True, lcc_detach=False, want_src_grad=True,
-                 alpha=0.85, smooth_weight=1e-3):
+                 alpha=0.85, smooth_weight=1e-3, chunks=3):
         self.lib = _lib.load()
         self.device = torch.device(device)
         flags = (_lib.F_LCC if lcc else 0) | (_lib.F_LCC_DETACH if lcc_detach else 0)
         if not want_src_grad:
             flags |= _lib.F_NO_SRC_GRAD
-        self.desc = _lib.make_desc(B, N, S, H, W, flags, alpha, smooth_weight)
-        n = ctypes.c_size_t()
-        _lib.check(self.lib.colvo_step_host_arena_bytes(ctypes.byref(self.desc), ctypes.byref(n)), "arena_bytes")
-        self.arena = torch.empty(n.value, dtype=torch.uint8, device=self.device)
+        chunks = max(1, min(int(chunks), B))
+        q, r = divmod(B, chunks)
+        sizes = [q + (1 if i < r else 0) for i in range(chunks)]
+        self.spans, lo = [], 0
+        for n in sizes:
+            self.spans.append((lo, lo + n))
+            lo += n
+        self.B, self.S = B, S
         pin = dict(dtype=torch.float32, pin_memory=True)
-        self.h_loss = torch.zeros(1, **pin)
+        self.h_loss_parts = torch.zeros(chunks, **pin)
         self.h_grad_depth = [torch.zeros(B, 1, H >> k, W >> k, **pin) for k in range(S)]
         self.h_grad_T = torch.zeros(B, N, 4, 4, **pin)
         self.h_grad_srcs = torch.zeros(B, N, 3, H, W, **pin) if want_src_grad else None
-        self.S = S
+        self.descs, self.arenas, self.streams = [], [], []
+        with torch.cuda.device(self.device):
+            for n in sizes:
+                d = _lib.make_desc(n, N, S, H, W, flags, alpha, smooth_weight)
+                nb = ctypes.c_size_t()
+                _lib.check(self.lib.colvo_step_host_arena_bytes(ctypes.byref(d), ctypes.byref(nb)), "arena_bytes")
+                self.descs.append(d)
+                self.arenas.append(torch.empty(nb.value, dtype=torch.uint8, device=self.device))
+                self.streams.append(torch.cuda.Stream(self.device))
+        self._done = [torch.cuda.Event() for _ in sizes]
 
     def h2d_bytes(self, depth, pose, K, tgt, srcs) -> int:
         return 4 * (tgt.numel() + srcs.numel() + sum(d.numel() for d in depth) + K.numel() + pose.numel())
 
     def d2h_bytes(self) -> int:
-        n = 1 + sum(g.numel() for g in self.h_grad_depth) + self.h_grad_T.numel()
+        n = len(self.spans) + sum(g.numel() for g in self.h_grad_depth) + self.h_grad_T.numel()
         if self.h_grad_srcs is not None:
             n += self.h_grad_srcs.numel()
         return 4 * n
 
-    def step(self, depth, pose, K, tgt, srcs, stream: Optional[torch.cuda.Stream] = None):
-        """Inputs are CPU tensors (pinned for full speed).  Enqueues everything on `stream`; the
-        host outputs are valid after `stream.synchronize()`."""
+    def step(self, depth, pose, K, tgt, srcs):
+        """Inputs are CPU tensors (pinned for full speed).  Enqueues every chunk on its own stream, ordered
+        after the caller's current stream; call `finish()` (or synchronise) before reading the host outputs."""
         for t in list(depth) + [pose, K, tgt, srcs]:
             if t.device.type != "cpu" or t.dtype != torch.float32 or not t.is_contiguous():
                 raise ValueError("HostStepper.step takes contiguous float32 CPU tensors")
-        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        cur = torch.cuda.current_stream(self.device)
         with torch.cuda.device(self.device):
-            rc = self.lib.colvo_photo_step_host(
-                ctypes.byref(self.desc), tgt.data_ptr(), srcs.data_ptr(), _lib.ptr_array([d.data_ptr() for d in depth]),
-                K.data_ptr(), pose.data_ptr(), self.h_loss.data_ptr(),
-                _lib.ptr_array([g.data_ptr() for g in self.h_grad_depth]), self.h_grad_T.data_ptr(),
-                self.h_grad_srcs.data_ptr() if self.h_grad_srcs is not None else None, self.arena.data_ptr(),
-                self.arena.numel(), st.cuda_stream)
-        _lib.check(rc, "colvo_photo_step_host")
-        return self.h_loss
+            for i, (lo, hi) in enumerate(self.spans):
+                st = self.streams[i]
+                st.wait_stream(cur)
+                rc = self.lib.colvo_photo_step_host(
+                    ctypes.byref(self.descs[i]), tgt[lo:hi].data_ptr(), srcs[lo:hi].data_ptr(),
+                    _lib.ptr_array([d[lo:hi].data_ptr() for d in depth]), K[lo:hi].data_ptr(), pose[lo:hi].data_ptr(),
+                    self.h_loss_parts[i:i + 1].data_ptr(), _lib.ptr_array([g[lo:hi].data_ptr() for g in self.h_grad_depth]),
+                    self.h_grad_T[lo:hi].data_ptr(),
+                    self.h_grad_srcs[lo:hi].data_ptr() if self.h_grad_srcs is not None else None,
+                    ctypes.c_float((hi - lo) / self.B), self.arenas[i].data_ptr(), self.arenas[i].numel(), st.cuda_stream)
+                _lib.check(rc, "colvo_photo_step_host")
+                self._done[i].record(st)
+        return self
+
+    def join(self):
+        """Make the caller's current stream wait for every chunk (for event timing); no host sync."""
+        cur = torch.cuda.current_stream(self.device)
+        for ev in self._done:
+            cur.wait_event(ev)
+
+    def finish(self) -> torch.Tensor:
+        """Synchronise all chunk streams and return the whole-batch mean loss (host tensor)."""
+        for st in self.streams:
+            st.synchronize()
+        w = torch.tensor([(hi - lo) / self.B for lo, hi in self.spans])
+        return (self.h_loss_parts * w).sum()

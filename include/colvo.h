@@ -109,15 +109,18 @@ int colvo_consistency(int32_t F, int32_t H, int32_t W, uint32_t flags, const flo
                       void* stream);
 
 /* End-to-end step on HOST buffers: H2D copies of the inputs (use pinned memory), forward,
- * backward with grad_loss = 1, D2H copies of loss and gradients, all on `stream`.
+ * backward with grad_loss = grad_scale, D2H copies of loss and gradients, all on `stream`.
  * `arena` is caller-owned DEVICE memory of colvo_step_host_arena_bytes bytes.
  * h_grad_srcs may be NULL with COLVO_F_NO_SRC_GRAD.  The call does not synchronise: the host
- * outputs are complete once `stream` has been synchronised.
+ * outputs are complete once `stream` has been synchronised.  A caller that splits a batch into
+ * chunks on several streams (to overlap H2D, compute and D2H) passes grad_scale = B_chunk / B and
+ * combines the chunk losses with the same weights.
  */
 int colvo_step_host_arena_bytes(const ColvoDesc* d, size_t* bytes);
 int colvo_photo_step_host(const ColvoDesc* d, const float* h_tgt, const float* h_srcs, const float* const* h_depth,
                           const float* h_K, const float* h_T, float* h_loss, float* const* h_grad_depth,
-                          float* h_grad_T, float* h_grad_srcs, void* arena, size_t arena_bytes, void* stream);
+                          float* h_grad_T, float* h_grad_srcs, float grad_scale, void* arena, size_t arena_bytes,
+                          void* stream);
 
 /* Profiling aid (bench.py's roofline leg): bracket the NEXT launch of one kernel with two
  * caller-owned cudaEvent_t on the launching stream.  One-shot, process-wide; pass

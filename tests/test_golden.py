@@ -1,0 +1,90 @@
+"""The oracle against the committed golden fixtures (tests/golden/*.npz, made by make_golden.py),
+and -- on the GPU box -- the CUDA path against the same files."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import photometric as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+FILES = sorted(glob.glob(os.path.join(HERE, "golden", "b*.npz")))
+KW = {"b1_16x24_nolcc": dict(lcc=False), "b1_16x24_detach": dict(lcc_detach=True, smooth_weight=0.05)}
+
+
+def load(path):
+    z = np.load(path)
+    t = {k: torch.from_numpy(z[k]) for k in z.files}
+    S = sum(1 for k in t if k.startswith("depth") and not k.startswith("grad"))
+    name = os.path.splitext(os.path.basename(path))[0]
+    return name, t, S
+
+
+def relinf(a, b):
+    return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
+
+
+def test_fixtures_exist():
+    assert len(FILES) == 5 and os.path.exists(os.path.join(HERE, "golden", "consistency_f6_24x32.npz"))
+
+
+@pytest.mark.parametrize("path", FILES, ids=[os.path.basename(f) for f in FILES])
+def test_oracle_reproduces_golden(path):
+    name, t, S = load(path)
+    depth = [t[f"depth{k}"].clone().requires_grad_() for k in range(S)]
+    pose = t["pose"].clone().requires_grad_()
+    srcs = t["srcs"].clone().requires_grad_()
+    loss, valid, sel, ab = O.photometric_loss(depth, pose, t["K"], t["tgt"], srcs, return_masks=True, **KW.get(name, {}))
+    loss.backward()
+    assert torch.equal(valid, t["valid"])
+    assert (t["gap"][sel != t["sel"]] < 1e-4).all()         # summation order may differ between CPUs
+    assert abs(loss.item() - t["loss"].item()) <= 1e-6 * abs(t["loss"].item()) + 1e-9
+    assert torch.allclose(ab, t["ab"], rtol=1e-5, atol=1e-6)
+    if torch.equal(sel, t["sel"]):
+        for k in range(S):
+            assert relinf(depth[k].grad, t[f"grad_depth{k}"]) < 1e-4
+        assert relinf(pose.grad, t["grad_pose"]) < 1e-4 and relinf(srcs.grad, t["grad_srcs"]) < 1e-4
+
+
+def test_oracle_consistency_reproduces_golden():
+    z = np.load(os.path.join(HERE, "golden", "consistency_f6_24x32.npz"))
+    t = {k: torch.from_numpy(z[k]) for k in z.files}
+    out = O.consistency(t["depth"], t["pose"], t["K"], t["frames"])
+    assert torch.allclose(out, t["out"], rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", FILES, ids=[os.path.basename(f) for f in FILES])
+def test_cuda_path_matches_golden(path):
+    import coivo_b200
+    name, t, S = load(path)
+    dev = "cuda:0"
+    depth = [t[f"depth{k}"].to(dev).requires_grad_() for k in range(S)]
+    pose = t["pose"].to(dev).requires_grad_()
+    srcs = t["srcs"].to(dev).requires_grad_()
+    loss, valid, sel, ab = coivo_b200.photometric_loss(depth, pose, t["K"].to(dev), t["tgt"].to(dev), srcs,
+                                                       return_masks=True, **KW.get(name, {}))
+    loss.backward()
+    assert torch.equal(valid.cpu(), t["valid"]), "valid must be bit-exact"
+    mism = sel.cpu() != t["sel"]
+    assert (t["gap"][mism] < 1e-4).all()
+    assert abs(loss.item() - t["loss"].item()) <= 1e-4 * abs(t["loss"].item())
+    assert torch.allclose(ab.cpu(), t["ab"], rtol=1e-5, atol=1e-6)
+    if not mism.any():       # gradients are comparable only under the same arg-min decisions
+        for k in range(S):
+            assert relinf(depth[k].grad.cpu(), t[f"grad_depth{k}"]) < 1e-4
+        assert relinf(pose.grad.cpu(), t["grad_pose"]) < 1e-4
+        assert relinf(srcs.grad.cpu(), t["grad_srcs"]) < 1e-4
+
+
+@pytest.mark.gpu
+def test_cuda_consistency_matches_golden():
+    import coivo_b200
+    z = np.load(os.path.join(HERE, "golden", "consistency_f6_24x32.npz"))
+    t = {k: torch.from_numpy(z[k]).to("cuda:0") for k in z.files}
+    out = coivo_b200.consistency(t["depth"], t["pose"], t["K"], t["frames"]).cpu()
+    ref = t["out"].cpu()
+    assert torch.equal(out[:, 3], ref[:, 3])
+    assert torch.allclose(out, ref, rtol=1e-4, atol=1e-6)

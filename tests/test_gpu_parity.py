@@ -165,16 +165,22 @@ def test_consistency_sweep_matches_oracle():
     assert torch.allclose(got2, ref2, rtol=1e-4, atol=1e-6)
 
 
-def test_host_stepper_matches_device_path():
+@pytest.mark.parametrize("chunks", [1, 2])
+def test_host_stepper_matches_device_path(chunks):
     d = make_triplets(2, 64, 96, seed=14)
-    st = coivo_b200.HostStepper(2, 2, 4, 64, 96, device=DEV)
+    st = coivo_b200.HostStepper(2, 2, 4, 64, 96, device=DEV, chunks=chunks)
     pin = lambda t: t.pin_memory()
-    h = st.step([pin(x) for x in d["depth"]], pin(d["pose"]), pin(d["K"]), pin(d["tgt"]), pin(d["srcs"]))
-    torch.cuda.synchronize()
+    st.step([pin(x) for x in d["depth"]], pin(d["pose"]), pin(d["K"]), pin(d["tgt"]), pin(d["srcs"]))
+    h = st.finish()
     loss, valid, sel, ab, gd, gT, gs = run_cuda(d)
-    assert abs(h.item() - loss.item()) < 1e-7
-    for k in range(4):
-        assert torch.equal(st.h_grad_depth[k], gd[k])
-    assert torch.equal(st.h_grad_T, gT)
+    assert abs(h.item() - loss.item()) < 1e-6
+    if chunks == 1:
+        for k in range(4):
+            assert torch.equal(st.h_grad_depth[k], gd[k])
+        assert torch.equal(st.h_grad_T, gT)
+    else:                                    # per-chunk scaling rounds differently in the last bit
+        for k in range(4):
+            assert relinf(st.h_grad_depth[k], gd[k]) < 1e-5
+        assert relinf(st.h_grad_T, gT) < 1e-5
     assert relinf(st.h_grad_srcs, gs) < 1e-5
-    assert st.d2h_bytes() == 4 * (1 + sum(x.numel() for x in gd) + gT.numel() + gs.numel())
+    assert st.d2h_bytes() == 4 * (chunks + sum(x.numel() for x in gd) + gT.numel() + gs.numel())
