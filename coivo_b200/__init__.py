@@ -6,6 +6,7 @@ PyTorch training loop calls (`photometric_loss`, `consistency`).  CUDA-only by d
 """
 from .loss import photometric_loss, HostStepper  # noqa: F401
 from .consistency import consistency  # noqa: F401
+from .graph import GraphedStep  # noqa: F401
 from . import dist, synthetic  # noqa: F401
 
-__all__ = ["photometric_loss", "consistency", "HostStepper", "dist", "synthetic"]
+__all__ = ["photometric_loss", "consistency", "HostStepper", "GraphedStep", "dist", "synthetic"]

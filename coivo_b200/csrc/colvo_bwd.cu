@@ -12,6 +12,9 @@
 //   k_pose_final     deterministic reduction of the pose-gradient partials
 #include "colvo_kernels.cuh"
 
+#ifndef COLVO_BWD_SLOTS     // 1: final pose reduction through smem slots; 0: fp64 shuffle trees
+#define COLVO_BWD_SLOTS 1
+#endif
 #ifndef COLVO_MINB_BWD      // CTAs per SM the register allocator must allow -- tuned on B200, see DESIGN.md
 #define COLVO_MINB_BWD 3
 #endif
@@ -195,18 +198,19 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_BWD)
         float du = 0.f, dv = 0.f;
         const float w00 = (1.f - t.wx) * (1.f - t.wy), w01 = t.wx * (1.f - t.wy);
         const float w10 = (1.f - t.wx) * t.wy, w11 = t.wx * t.wy;
-        const int o00 = t.y0 * P.W + t.x0, o01 = t.y0 * P.W + t.x1, o10 = t.y1 * P.W + t.x0, o11 = t.y1 * P.W + t.x1;
         float* gs = grad_srcs ? grad_srcs + (long long)b * P.src_bs + (long long)n * P.src_ns : nullptr;
+        float *g00 = gs + (t.y0 * P.W + t.x0), *g01 = gs + (t.y0 * P.W + t.x1);
+        float *g10 = gs + (t.y1 * P.W + t.x0), *g11 = gs + (t.y1 * P.W + t.x1);
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
           du += hq[ch] * ((1.f - t.wy) * (tx4.i01[ch] - tx4.i00[ch]) + t.wy * (tx4.i11[ch] - tx4.i10[ch]));
           dv += hq[ch] * ((1.f - t.wx) * (tx4.i10[ch] - tx4.i00[ch]) + t.wx * (tx4.i11[ch] - tx4.i01[ch]));
           if (gs) {
-            const int co = ch * P.HW;
-            atomicAdd(gs + (co + o00), w00 * hq[ch]);
-            atomicAdd(gs + (co + o01), w01 * hq[ch]);
-            atomicAdd(gs + (co + o10), w10 * hq[ch]);
-            atomicAdd(gs + (co + o11), w11 * hq[ch]);
+            atomicAdd(g00, w00 * hq[ch]);
+            atomicAdd(g01, w01 * hq[ch]);
+            atomicAdd(g10, w10 * hq[ch]);
+            atomicAdd(g11, w11 * hq[ch]);
+            g00 += P.HW; g01 += P.HW; g10 += P.HW; g11 += P.HW;
           }
         }
         if (!t.gx) du = 0.f;
@@ -234,6 +238,19 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_BWD)
 
   // ---- per-tile pose-gradient partials (fp64: sums of terms of both signs) ----
   const int blk = (b * P.tiles_y + blockIdx.y) * P.tiles_x + blockIdx.x;
+#if COLVO_BWD_SLOTS
+  __syncthreads();                                   // the coefficient buffers are free: reuse them as slot storage
+  float* slots = reinterpret_cast<float*>(smem_raw); // [NS*12][kThreads] <= 24 KB of the 32 KB coefficient area
+#pragma unroll
+  for (int n = 0; n < NS; ++n) {
+    float gp[12];
+    pose_grad_expand(pw[n], pt[n], own_rx, own_ry, gp);
+#pragma unroll
+    for (int j = 0; j < 12; ++j) slots[(n * 12 + j) * kThreads + tid] = in_img ? gp[j] : 0.f;
+  }
+  __syncthreads();
+  block_sum_slots<NS * 12>(slots, red, [&](int slot, double v) { pose_part[(long long)blk * (NS * 12) + slot] = v; });
+#else
   const int lane = tid & 31, wid = tid >> 5;
 #pragma unroll
   for (int n = 0; n < NS; ++n) {
@@ -252,6 +269,7 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_BWD)
     for (int w = 0; w < kThreads / 32; ++w) s += red[w * (NS * 12) + tid];
     pose_part[(long long)blk * (NS * 12) + tid] = s;
   }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------
@@ -306,17 +324,30 @@ __global__ void __launch_bounds__(kThreads)
     if (i == hk - 1) v_hi = P.H - 1;   // clamped border rows / columns all land on the last texel
     if (j == wk - 1) u_hi = P.W - 1;
     const int sr = sub / G, sc = sub - sr * G;
-    for (int v = v_lo + sr; v <= v_hi; v += G) {
-      Axis ay = upsample_axis(v, ry, hk);
-      float wy = ((ay.i0 == i) ? (1.0f - ay.w1) : 0.f) + ((ay.i1 == i) ? ay.w1 : 0.f);
-      if (wy == 0.f) continue;
-      float row = 0.f;
-      for (int u = u_lo + sc; u <= u_hi; u += G) {
-        Axis ax = upsample_axis(u, rx, wk);
-        float wx = ((ax.i0 == j) ? (1.0f - ax.w1) : 0.f) + ((ax.i1 == j) ? ax.w1 : 0.f);
-        if (wx != 0.f) row = fmaf(wx, __ldg(dD + v * P.W + u), row);
+    // the column weights do not depend on the row: compute them once per block of 8 columns of this lane
+    for (int ub = u_lo + sc; ub <= u_hi; ub += 8 * G) {
+      float wxs[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int u = ub + c * G;
+        float wx = 0.f;
+        if (u <= u_hi) {
+          Axis ax = upsample_axis(u, rx, wk);
+          wx = ((ax.i0 == j) ? (1.0f - ax.w1) : 0.f) + ((ax.i1 == j) ? ax.w1 : 0.f);
+        }
+        wxs[c] = wx;
       }
-      acc = fmaf(wy, row, acc);
+      for (int v = v_lo + sr; v <= v_hi; v += G) {
+        Axis ay = upsample_axis(v, ry, hk);
+        const float wy = ((ay.i0 == i) ? (1.0f - ay.w1) : 0.f) + ((ay.i1 == i) ? ay.w1 : 0.f);
+        if (wy == 0.f) continue;
+        const float* rowp = dD + v * P.W + ub;
+        float row = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          if (wxs[c] != 0.f) row = fmaf(wxs[c], __ldg(rowp + c * G), row);
+        acc = fmaf(wy, row, acc);
+      }
     }
   }
   for (int o = L >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);

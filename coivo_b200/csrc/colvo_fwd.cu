@@ -17,6 +17,9 @@
 #ifndef COLVO_MINB_STATS
 #define COLVO_MINB_STATS 4
 #endif
+#ifndef COLVO_FWD_SLOTS     // 1: park dL/da, dL/db terms in smem slots and sum once; 0: fp64 shuffle tree per scale
+#define COLVO_FWD_SLOTS 0
+#endif
 #ifndef COLVO_Y_REGS        // 1: keep the 3x3 target window of the own pixel in registers (27 regs)
 #define COLVO_Y_REGS 0
 #endif
@@ -261,6 +264,9 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_FWD)
   constexpr int NV = 1 + NS * kMaxS * 2;
   __shared__ float ys[3 * kFN];
   __shared__ float xs[2][3 * kFN];
+#if COLVO_FWD_SLOTS
+  __shared__ float slots[NV * kThreads];            // per-thread loss / dL/da / dL/db terms, summed once at the end
+#endif
   __shared__ double red[(kThreads / 32) * NV];
 
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
@@ -309,8 +315,15 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_FWD)
   }
 
   float loss_acc = 0.f;
+#if COLVO_FWD_SLOTS
+  if (need_g) {
+#pragma unroll
+    for (int i = 1; i < NV; ++i) slots[i * kThreads + tid] = 0.f;            // slots of unused scales stay 0
+  }
+#else
   const int lane = tid & 31, wid = tid >> 5;
   for (int i = tid; i < (kThreads / 32) * NV; i += kThreads) red[i] = 0.0;   // slots of unused scales stay 0
+#endif
 
 #pragma unroll
   for (int k = 0; k < kMaxS; ++k) {
@@ -361,25 +374,43 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_FWD)
           }
         }
       }
-      // dL/da, dL/db of this scale: sums of large terms of both signs -> reduce in fp64 right away
-      // (each slot is written exactly once per warp, so no accumulator registers are carried)
+      // dL/da, dL/db terms of this scale: parked in shared memory (own slot per thread, no accumulator
+      // registers); summed in fp64 at the end -- they are large terms of both signs
       if (need_g) {
 #pragma unroll
         for (int n = 0; n < NS; ++n) {
           const bool w = in_img && sel == NS + n;
+#if COLVO_FWD_SLOTS
+          slots[(1 + (n * kMaxS + k) * 2 + 0) * kThreads + tid] = w ? dpa[n] * (1.0f / 3.0f) : 0.f;
+          slots[(1 + (n * kMaxS + k) * 2 + 1) * kThreads + tid] = w ? dpb[n] * (1.0f / 3.0f) : 0.f;
+#else
+          // reduce in fp64 right away: each slot is written exactly once per warp, no accumulator registers
           double sa = warp_sum(w ? (double)(dpa[n] * (1.0f / 3.0f)) : 0.0);
           double sb = warp_sum(w ? (double)(dpb[n] * (1.0f / 3.0f)) : 0.0);
           if (lane == 0) {
             red[wid * NV + 1 + (n * kMaxS + k) * 2 + 0] = sa;
             red[wid * NV + 1 + (n * kMaxS + k) * 2 + 1] = sb;
           }
+#endif
         }
       }
     }
   }
 
-  // Per-tile partials (thread i < NV sums the 8 per-warp values of slot i).
+  // Per-tile partials: slot 0 = loss, slots 1.. = dL/da, dL/db per warped frame.
   const int blk = (b * P.tiles_y + blockIdx.y) * P.tiles_x + blockIdx.x;
+#if COLVO_FWD_SLOTS
+  slots[tid] = loss_acc;
+  __syncthreads();
+  if (need_g) {
+    block_sum_slots<NV>(slots, red, [&](int slot, double v) {
+      if (slot == 0) loss_part[blk] = v;
+      else g_part[(long long)blk * (NS * kMaxS * 2) + (slot - 1)] = v;
+    });
+  } else {
+    block_sum_slots<1>(slots, red, [&](int, double v) { loss_part[blk] = v; });
+  }
+#else
   {
     double s = warp_sum((double)loss_acc);
     if (lane == 0) red[wid * NV] = s;
@@ -392,6 +423,7 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_FWD)
     if (tid == 0) loss_part[blk] = s;
     else g_part[(long long)blk * (NS * kMaxS * 2) + (tid - 1)] = s;
   }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------

@@ -87,14 +87,18 @@ __device__ __forceinline__ void warp_sample(const KP& P, const float* __restrict
   g = reproject_ray(rx, ry, D, cam, pose, P.W, P.H, P.eps_proj, P.z_min);
   t = make_taps(g.u, g.v, P.W, P.H);
   const int r0 = t.y0 * P.W, r1 = t.y1 * P.W;
-  const int o00 = r0 + t.x0, o01 = r0 + t.x1, o10 = r1 + t.x0, o11 = r1 + t.x1;
+  // one IMAD.WIDE per address: four tap pointers, then + HW per channel plane
+  const float* p00 = src + (r0 + t.x0);
+  const float* p01 = src + (r0 + t.x1);
+  const float* p10 = src + (r1 + t.x0);
+  const float* p11 = src + (r1 + t.x1);
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    const int co = c * P.HW;
-    tx.i00[c] = __ldg(src + (co + o00));
-    tx.i01[c] = __ldg(src + (co + o01));
-    tx.i10[c] = __ldg(src + (co + o10));
-    tx.i11[c] = __ldg(src + (co + o11));
+    tx.i00[c] = __ldg(p00);
+    tx.i01[c] = __ldg(p01);
+    tx.i10[c] = __ldg(p10);
+    tx.i11[c] = __ldg(p11);
+    p00 += P.HW; p01 += P.HW; p10 += P.HW; p11 += P.HW;
   }
 #pragma unroll
   for (int c = 0; c < 3; ++c) x[c] = bilerp(tx.i00[c], tx.i01[c], tx.i10[c], tx.i11[c], t.wx, t.wy);
@@ -126,6 +130,32 @@ __device__ __forceinline__ void block_reduce_store(TV (&v)[NV], TV* sm /* [kThre
 #pragma unroll
     for (int w = 0; w < kThreads / 32; ++w) s += sm[w * NV + threadIdx.x];
     out[threadIdx.x] = s;
+  }
+}
+
+// Deterministic block sum of NSLOT per-thread fp32 values that already sit in shared memory as
+// slots[s * kThreads + tid]: (slot, warp) pairs are summed in fp64 by one thread each (lane-rotated
+// reads: conflict-free), then 8 warp partials per slot are combined in a fixed order.  ~5x fewer
+// issue slots than NSLOT fp64 shuffle trees.  `part` is (kThreads/32) * NSLOT doubles of scratch.
+// Call with all threads after the slots are written and a __syncthreads(); result in out[s], s < NSLOT.
+template <int NSLOT, typename F>
+__device__ __forceinline__ void block_sum_slots(const float* slots, double* part, F&& emit) {
+  constexpr int NW = kThreads / 32;
+  const int tid = threadIdx.x;
+  for (int item = tid; item < NSLOT * NW; item += kThreads) {
+    const int s = item / NW, w = item - s * NW;
+    const float* p = slots + s * kThreads + w * 32;
+    double acc = 0.0;
+#pragma unroll 8
+    for (int l = 0; l < 32; ++l) acc += (double)p[(l + tid) & 31];
+    part[item] = acc;
+  }
+  __syncthreads();
+  if (tid < NSLOT) {
+    double acc = 0.0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) acc += part[tid * NW + w];
+    emit(tid, acc);
   }
 }
 
