@@ -112,8 +112,10 @@ size_t carve_saved(const ColvoDesc* d, double* saved, SavedView& sv) {
       sv.s_field[k] = nullptr;
     }
   }
+  nf = (nf + 3) / 4 * 4;                       // 16-byte texels (the doubles in front keep the base 16 B aligned)
+  if ((nd & 1) != 0) nf += 2;                  // ... also when the double count is odd
   sv.coef = f ? f + nf : nullptr;
-  nf += (size_t)d->B * d->S * 9 * d->H * d->W;
+  nf += (size_t)d->B * d->S * 12 * d->H * d->W;
   return nd + (nf + 1) / 2;
 }
 
@@ -179,7 +181,7 @@ int colvo_photo_forward(const ColvoDesc* d, const float* tgt, const float* srcs,
   for (int k = 0; k < d->S; ++k)
     if (!depth[k]) return COLVO_E_NULL_PTR;
   if ((d->flags & COLVO_F_SAVE_FOR_BWD) && (!sel || !saved)) return COLVO_E_NULL_PTR;
-  if (((uintptr_t)ws & 255u) || ((uintptr_t)saved & 7u)) return COLVO_E_MISALIGNED;
+  if (((uintptr_t)ws & 255u) || ((uintptr_t)saved & 15u)) return COLVO_E_MISALIGNED;
   FwdBuffers F;
   if (carve_fwd(d, ws, F) > ws_bytes) return COLVO_E_WORKSPACE;
   KP P;
@@ -203,7 +205,7 @@ int colvo_photo_backward(const ColvoDesc* d, const float* tgt, const float* srcs
     if (!depth[k] || !grad_depth[k]) return COLVO_E_NULL_PTR;
   const bool want_src = !(d->flags & COLVO_F_NO_SRC_GRAD);
   if (want_src && !grad_srcs) return COLVO_E_NULL_PTR;
-  if (((uintptr_t)ws & 255u) || ((uintptr_t)saved & 7u)) return COLVO_E_MISALIGNED;
+  if (((uintptr_t)ws & 255u) || ((uintptr_t)saved & 15u)) return COLVO_E_MISALIGNED;
   BwdBuffers Bw;
   if (carve_bwd(d, ws, Bw) > ws_bytes) return COLVO_E_WORKSPACE;
   KP P;

@@ -24,15 +24,6 @@ namespace colvo {
 constexpr int kCH = kTileH + 2, kCW = kTileW + 2;   // tile + 1-pixel halo (window centres)
 constexpr int kCN = kCH * kCW;
 
-// 4-byte asynchronous global->shared copy (LDGSTS); zero-fills the destination when !pred
-__device__ __forceinline__ void cp_async4(float* smem, const float* gmem, bool pred) {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  const int sz = pred ? 4 : 0;
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(sa), "l"(gmem), "r"(sz));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
-
 // smoothness gradient of one depth texel from the saved adjoint field (grad_loss folded in by the caller)
 __device__ __forceinline__ float smooth_grad(float s, float D, float inv, float corr) {
   const float dr = 1.0f / D;
@@ -127,15 +118,15 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_BWD)
   // Coefficient tile of scale k (+1 halo; zeros where no re-projection won or outside the image), fetched with
   // cp.async one scale ahead so its global latency hides behind the previous scale's arithmetic.
   auto stage_coef = [&](int k) {
-    float* cbf = reinterpret_cast<float*>(coef[k & 1]);
-    const float* cin = coef_in + ((long long)(b * P.S + k) * 9) * P.HW;
+    float4* cbf = coef[k & 1];
+    const float4* cin = reinterpret_cast<const float4*>(coef_in) + (long long)(b * P.S + k) * P.HW * 3;
     for (int idx = tid; idx < kCN; idx += kThreads) {
       const int r = idx / kCW, c = idx - r * kCW;
       const unsigned char sv = sels[k][idx];
       const bool on = sv != 255 && sv >= NS;
-      const float* p = on ? cin + (y0 - 1 + r) * P.W + (x0 - 1 + c) : cin;
+      const float4* p = on ? cin + ((y0 - 1 + r) * P.W + (x0 - 1 + c)) * 3 : cin;
 #pragma unroll
-      for (int f = 0; f < 9; ++f) cp_async4(cbf + (idx * 3 + f / 3) * 4 + f % 3, p + f * P.HW, on);
+      for (int ch = 0; ch < 3; ++ch) cp_async16(cbf + idx * 3 + ch, p + ch, on);
     }
     cp_async_commit();
   };

@@ -49,27 +49,31 @@ static inline int total_chunks(const KP& P) {
 }
 
 // ------------------------------------------------------------------------------------------
-// blocks [0, n_pyr): target pyramid (grid-stride);  blocks [n_pyr, ...): sum of 1/D chunks
+// blocks [0, n_pyr): target pyramid, one thread per output texel (block ranges per scale: pyr_off[k]);
+// blocks [n_pyr, ...): sum of 1/D chunks
+struct PyrOff { int off[kMaxS + 1]; };
 __global__ void __launch_bounds__(kThreads)
-    k_prepass(KP P, int n_pyr, float* p1, float* p2, float* p3, double* __restrict__ disp_part) {
+    k_prepass(KP P, int n_pyr, PyrOff po, float* p1, float* p2, float* p3, double* __restrict__ disp_part) {
   __shared__ double sm[kThreads / 32];
   if ((int)blockIdx.x < n_pyr) {
-    for (int k = 1; k < P.S; ++k) {
-      float* out = (k == 1) ? p1 : (k == 2 ? p2 : p3);
-      const int hk = P.h[k], wk = P.w[k], f = 1 << k;
-      const int total = P.B * 3 * hk * wk;
-      const float inv = 1.0f / (float)(f * f);
-      for (int i = blockIdx.x * kThreads + threadIdx.x; i < total; i += n_pyr * kThreads) {
-        int x = i % wk, r = i / wk;
-        int y = r % hk, bc = r / hk;
-        int b = bc / 3, c = bc - 3 * b;
-        const float* src = P.tgt + (long long)b * P.tgt_bs + (long long)c * P.HW + (y * f) * P.W + x * f;
-        float s = 0.f;
-        for (int dy = 0; dy < f; ++dy)
-          for (int dx = 0; dx < f; ++dx) s += __ldg(src + dy * P.W + dx);
-        out[i] = s * inv;
-      }
+    int k = 1;
+    while (k + 1 < P.S && (int)blockIdx.x >= po.off[k + 1]) ++k;
+    float* out = (k == 1) ? p1 : (k == 2 ? p2 : p3);
+    const int hk = P.h[k], wk = P.w[k], f = 1 << k;
+    const int total = P.B * 3 * hk * wk;
+    const int i = (blockIdx.x - po.off[k]) * kThreads + threadIdx.x;
+    if (i >= total) return;
+    const int x = i % wk, r = i / wk;
+    const int y = r % hk, bc = r / hk;
+    const int b = bc / 3, c = bc - 3 * b;
+    const float* src = P.tgt + (long long)b * P.tgt_bs + (long long)c * P.HW + (y * f) * P.W + x * f;
+    float s = 0.f;
+    for (int dy = 0; dy < f; ++dy) {
+      float rs = 0.f;
+      for (int dx = 0; dx < f; ++dx) rs += __ldg(src + dy * P.W + dx);
+      s += rs;
     }
+    out[i] = s * (1.0f / (float)(f * f));
     return;
   }
   int b, k, c;
@@ -77,7 +81,7 @@ __global__ void __launch_bounds__(kThreads)
   const int n = P.h[k] * P.w[k], C = P.sm_chunks[k];
   const float* D = P.depth[k] + (long long)b * P.depth_bs[k];
   double acc = 0.0;
-  for (int i = c * kThreads + threadIdx.x; i < n; i += C * kThreads) acc += (double)(1.0f / __ldg(D + i));
+  for (int i = c * kThreads + threadIdx.x; i < n; i += C * kThreads) acc += (double)f_rcp(__ldg(D + i));
   double v[1] = {acc};
   block_reduce_store<1, double>(v, sm, disp_part + ((long long)(b * P.S + k)) * kSmoothMaxChunks + c);
 }
@@ -191,7 +195,8 @@ __global__ void __launch_bounds__(32)
 // The fused tile kernel.  One CTA = one 32x8 output tile of one triplet; the (k, n) loops run
 // inside the CTA so the target tile, its SSIM moments and the identity candidates are computed
 // once and shared by all 2*S warped frames.  The warped tile (+1 halo, read from the frames
-// k_warp_stats left in scratch) is double-buffered in shared memory: one __syncthreads per frame.
+// k_warp_stats left in scratch) is double-buffered in shared memory and fetched one frame ahead with
+// cp.async: one __syncthreads per frame, global latency hidden behind the previous frame's SSIM.
 constexpr int kFH = kTileH + 2, kFW = kTileW + 2;   // tile + 1-pixel SSIM halo
 constexpr int kFN = kFH * kFW;
 
@@ -287,6 +292,27 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_FWD)
     pso[j] = idx;
     pgo[j] = reflect_clamp(y0 - 1 + r, P.H) * P.W + reflect_clamp(x0 - 1 + c, P.W);
   }
+  // Frame sequence of this tile: f < NS the raw sources (identity candidates), then f = NS + k*NS + n the
+  // warped frames.  Frame f+1 is fetched with cp.async into the other buffer while frame f is evaluated.
+  auto stage = [&](int f) {
+    const float* p;
+    if (f < NS) {
+      p = P.srcs + (long long)b * P.src_bs + (long long)f * P.src_ns;
+    } else {
+      const int k = (f - NS) / NS, n = (f - NS) % NS;
+      p = iw + (long long)((b * P.N + n) * P.S + k) * 3 * P.HW;
+    }
+    float* xb = xs[f & 1];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+      if (pok[j]) {
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) cp_async4(xb + ch * kFN + pso[j], p + (ch * P.HW + pgo[j]), true);
+      }
+    cp_async_commit();
+  };
+  const int n_frames = NS + P.S * NS;
+  stage(0);
 #pragma unroll
   for (int j = 0; j < 2; ++j)
     if (pok[j]) {
@@ -302,15 +328,10 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_FWD)
   float ident[NS];
 #pragma unroll
   for (int n = 0; n < NS; ++n) {
-    const float* src = P.srcs + (long long)b * P.src_bs + (long long)n * P.src_ns;
-    float* xb = xs[n & 1];
-#pragma unroll
-    for (int j = 0; j < 2; ++j)
-      if (pok[j]) {
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) xb[ch * kFN + pso[j]] = __ldg(src + (ch * P.HW + pgo[j]));
-      }
-    __syncthreads();
+    const float* xb = xs[n & 1];
+    cp_async_wait_all();
+    __syncthreads();              // frame n landed everywhere; everyone is done with the other buffer
+    if (n + 1 < n_frames) stage(n + 1);
     ident[n] = in_img ? pe_own(xb, yw, 1.0f, 0.0f, P) : 0.f;
   }
 
@@ -339,15 +360,11 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_FWD)
       for (int n = 0; n < NS; ++n) {
         const int bnk = (b * P.N + n) * P.S + k;
         const float a = __ldg(ab + 2 * bnk), bb = __ldg(ab + 2 * bnk + 1);
-        const float* wsrc = iw + (long long)bnk * 3 * P.HW;
-        float* xb = xs[(NS + k * NS + n) & 1];
-#pragma unroll
-        for (int j = 0; j < 2; ++j)
-          if (pok[j]) {
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) xb[ch * kFN + pso[j]] = __ldg(wsrc + (ch * P.HW + pgo[j]));
-          }
-        __syncthreads();
+        const int f = NS + k * NS + n;
+        const float* xb = xs[f & 1];
+        cp_async_wait_all();
+        __syncthreads();          // frame f landed everywhere; everyone is done with the other buffer
+        if (f + 1 < n_frames) stage(f + 1);
         dpa[n] = 0.f;
         dpb[n] = 0.f;
         if (in_img) {
@@ -363,13 +380,9 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_FWD)
         for (int n = 0; n < NS; ++n) {
           if (sel == NS + n) {
             if (coef_out) {     // the backward reads these only where sel says a re-projection won
-              float* co = coef_out + ((long long)(b * P.S + k) * 9) * P.HW + py * P.W + px;
+              float4* co = reinterpret_cast<float4*>(coef_out) + ((long long)(b * P.S + k) * P.HW + py * P.W + px) * 3;
 #pragma unroll
-              for (int ch = 0; ch < 3; ++ch) {
-                co[(3 * ch + 0) * (long long)P.HW] = cf[n][ch].ca;
-                co[(3 * ch + 1) * (long long)P.HW] = cf[n][ch].cb;
-                co[(3 * ch + 2) * (long long)P.HW] = cf[n][ch].cg;
-              }
+              for (int ch = 0; ch < 3; ++ch) co[ch] = make_float4(cf[n][ch].ca, cf[n][ch].cb, cf[n][ch].cg, 0.f);
             }
           }
         }
@@ -464,15 +477,15 @@ __global__ void __launch_bounds__(kThreads)
   double acc[3] = {0.0, 0.0, 0.0};
   for (int i = c * kThreads + threadIdx.x; i < n; i += C * kThreads) {
     const int y = i / wk, x = i - y * wk;
-    const float dr = 1.0f / __ldg(D + i);
+    const float dr = f_rcp(__ldg(D + i));
     const float d = dr * inv;
     const float i0 = __ldg(I + i), i1 = __ldg(I + cs + i), i2 = __ldg(I + 2 * cs + i);
     float s = 0.f;
     auto edge = [&](int j) -> float2 {   // (d_i - d_j, exp(-mean_c |I_i - I_j|))
-      float dn = (1.0f / __ldg(D + j)) * inv;
+      float dn = f_rcp(__ldg(D + j)) * inv;
       float e = (fabsf(i0 - __ldg(I + j)) + fabsf(i1 - __ldg(I + cs + j)) + fabsf(i2 - __ldg(I + 2 * cs + j))) *
                 (1.0f / 3.0f);
-      return make_float2(d - dn, expf(-e));
+      return make_float2(d - dn, __expf(-e));   // e in [0, 1]: MUFU.EX2 path, rel. error ~1e-6
     };
     if (x + 1 < wk) {
       float2 t = edge(i + 1);
@@ -653,8 +666,15 @@ cudaError_t launch_forward(const KP& P, const FwdBuffers& Wk, float* loss, float
   const int need_g = (save && lcc && !(P.flags & 2u)) ? 1 : 0;
   const int BNS = P.B * P.N * P.S;
   const int chunks = P.B * total_chunks(P);
-  const int n_pyr = (P.S > 1) ? imin(div_up(P.B * 3 * P.h[1] * P.w[1], kThreads), 148 * 4) : 0;
-  k_prepass<<<n_pyr + chunks, kThreads, 0, st>>>(P, n_pyr, Wk.pyr[1], Wk.pyr[2], Wk.pyr[3], Wk.disp_part);
+  PyrOff po;
+  int n_pyr = 0;
+  po.off[0] = 0;
+  for (int k = 1; k <= kMaxS; ++k) {
+    if (k < kMaxS) po.off[k] = n_pyr;
+    else po.off[kMaxS] = n_pyr;
+    if (k < P.S) n_pyr += div_up(P.B * 3 * P.h[k] * P.w[k], kThreads);
+  }
+  k_prepass<<<n_pyr + chunks, kThreads, 0, st>>>(P, n_pyr, po, Wk.pyr[1], Wk.pyr[2], Wk.pyr[3], Wk.disp_part);
   {
     ScopedKernelTimer tm(3, st);
     dim3 g(Wk.stat_chunks, P.B * P.S);

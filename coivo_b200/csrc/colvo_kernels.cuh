@@ -14,13 +14,14 @@ constexpr int kTileW = 32;       // one warp = one tile row: coalesced 128 B row
 constexpr int kTileH = 8;
 constexpr int kStatPPT = 8;      // pixels per thread in the LCC statistics pass
 constexpr int kSmoothMaxChunks = 64;
-constexpr int kSmoothPixPerBlock = 2048;
+constexpr int kSmoothPixPerBlock = 1024;
 
 // saved[] layout: doubles  [B*N*S][kSavedPerFrame]  n, mean_x, mean_y, 1/(n (var+eps)), a, b, G_a, G_b
 //                 doubles  [B*S][kSavedPerScale]    mean inverse depth, sum_p s_p d_p
 //                 floats   s-field of every scale   dL_smooth/dd*_p for grad_loss = 1, [B,h_k,w_k]
-//                 floats   [B,S,9,H,W]              SSIM adjoint coefficients (ca, cb, cg per channel) of the
-//                                                   winning re-projection candidate (undefined where identity won)
+//                 float4   [B,S,H,W,3]              SSIM adjoint coefficients (ca, cb, cg, -) per channel of the
+//                                                   winning re-projection candidate (undefined where identity won);
+//                                                   16-byte texels so the backward stages them with 16 B cp.async
 constexpr int kSavedPerFrame = 8;
 constexpr int kSavedPerScale = 2;
 
@@ -104,6 +105,21 @@ __device__ __forceinline__ void warp_sample(const KP& P, const float* __restrict
   for (int c = 0; c < 3; ++c) x[c] = bilerp(tx.i00[c], tx.i01[c], tx.i10[c], tx.i11[c], t.wx, t.wy);
 }
 
+// 4-byte asynchronous global->shared copy (LDGSTS); zero-fills the destination when !pred
+__device__ __forceinline__ void cp_async4(float* smem, const float* gmem, bool pred) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  const int sz = pred ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(sa), "l"(gmem), "r"(sz));
+}
+// 16-byte variant, L2-only (.cg): streaming data that should not displace the texels in L1
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool pred) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  const int sz = pred ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -178,7 +194,7 @@ struct SavedView {       // the caller-owned `saved` buffer, carved
   double* frame;         // [B*N*S][kSavedPerFrame]
   double* scale;         // [B*S][kSavedPerScale]
   float* s_field[kMaxS]; // [B,h_k,w_k]
-  float* coef;           // [B,S,9,H,W] unit-weight SSIM adjoint coefficients of the winning re-projection
+  float* coef;           // [B,S,H,W,3] float4: unit-weight SSIM adjoint coefficients of the winning re-projection
 };
 
 // one-shot event bracket around one kernel launch (colvo_debug_time_kernel)

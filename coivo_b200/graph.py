@@ -34,6 +34,11 @@ class GraphedStep:
         torch.cuda.synchronize(dev)
         for t in self._leaves:
             t.grad = None
+        # the leaves' AccumulateGrad nodes were created on the warm-up stream; capture runs on its own stream
+        try:
+            torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+        except AttributeError:
+            pass
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.loss = photometric_loss(self.depth, self.pose, self.K, self.tgt, self.srcs, **self.kw)
