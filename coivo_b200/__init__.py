@@ -7,6 +7,8 @@ PyTorch training loop calls (`photometric_loss`, `consistency`).  CUDA-only by d
 from .loss import photometric_loss, HostStepper  # noqa: F401
 from .consistency import consistency  # noqa: F401
 from .graph import GraphedStep  # noqa: F401
+from .frontend import disp_to_depth, photometric_loss_raw, poses_from_parameters  # noqa: F401
 from . import dist, synthetic  # noqa: F401
 
-__all__ = ["photometric_loss", "consistency", "HostStepper", "GraphedStep", "dist", "synthetic"]
+__all__ = ["photometric_loss", "consistency", "HostStepper", "GraphedStep", "poses_from_parameters", "disp_to_depth",
+           "photometric_loss_raw", "dist", "synthetic"]

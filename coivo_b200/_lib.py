@@ -15,7 +15,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 # COLVO_LIB selects another build of the same sources (tuning experiments); the default is the in-tree library
 LIB_PATH = os.environ.get("COLVO_LIB") or os.path.join(PKG_DIR, "libcolvo_b200.so")
-SOURCES = ["colvo_fwd.cu", "colvo_bwd.cu", "colvo_api.cu"]
+SOURCES = ["colvo_fwd.cu", "colvo_bwd.cu", "colvo_api.cu", "colvo_front.cu"]
 HEADERS = ["colvo_math.cuh", "colvo_kernels.cuh", os.path.join("..", "..", "include", "colvo.h")]
 
 # flags (include/colvo.h)
@@ -38,7 +38,7 @@ class ColvoDesc(ctypes.Structure):
         ("h", ctypes.c_int32 * MAX_SCALES), ("w", ctypes.c_int32 * MAX_SCALES),
         ("alpha", ctypes.c_float), ("c1", ctypes.c_float), ("c2", ctypes.c_float), ("eps_proj", ctypes.c_float),
         ("eps_lcc", ctypes.c_float), ("eps_disp", ctypes.c_float), ("z_min", ctypes.c_float),
-        ("smooth_weight", ctypes.c_float), ("flags", ctypes.c_uint32),
+        ("smooth_weight", ctypes.c_float), ("geo_weight", ctypes.c_float), ("flags", ctypes.c_uint32),
     ]
 
 
@@ -89,10 +89,10 @@ _SIGS = {
     "colvo_desc_init": (ctypes.c_int, [ctypes.POINTER(ColvoDesc)] + [ctypes.c_int32] * 5 + [ctypes.c_uint32]),
     "colvo_workspace_bytes": (ctypes.c_int, [ctypes.POINTER(ColvoDesc), ctypes.POINTER(ctypes.c_size_t)]),
     "colvo_saved_doubles": (ctypes.c_int, [ctypes.POINTER(ColvoDesc), ctypes.POINTER(ctypes.c_size_t)]),
-    "colvo_photo_forward": (ctypes.c_int, [ctypes.POINTER(ColvoDesc), _vp, _vp, ctypes.POINTER(_vp), _vp, _vp, _vp, _vp,
+    "colvo_photo_forward": (ctypes.c_int, [ctypes.POINTER(ColvoDesc), _vp, _vp, ctypes.POINTER(_vp), _vp, _vp, _vp, _vp, _vp,
                                            _vp, _vp, _vp, _vp, ctypes.c_size_t, _vp]),
-    "colvo_photo_backward": (ctypes.c_int, [ctypes.POINTER(ColvoDesc), _vp, _vp, ctypes.POINTER(_vp), _vp, _vp, _vp, _vp,
-                                            _vp, ctypes.POINTER(_vp), _vp, _vp, _vp, ctypes.c_size_t, _vp]),
+    "colvo_photo_backward": (ctypes.c_int, [ctypes.POINTER(ColvoDesc), _vp, _vp, ctypes.POINTER(_vp), _vp, _vp, _vp, _vp, _vp,
+                                            _vp, ctypes.POINTER(_vp), _vp, _vp, _vp, _vp, ctypes.c_size_t, _vp]),
     "colvo_consistency_workspace_bytes": (ctypes.c_int, [ctypes.c_int32] * 3 + [ctypes.POINTER(ctypes.c_size_t)]),
     "colvo_consistency": (ctypes.c_int, [ctypes.c_int32] * 3 + [ctypes.c_uint32, _vp, _vp, _vp, _vp, ctypes.c_int32,
                                                                  _vp, _vp, ctypes.c_size_t, _vp]),
@@ -100,6 +100,14 @@ _SIGS = {
     "colvo_photo_step_host": (ctypes.c_int, [ctypes.POINTER(ColvoDesc), _vp, _vp, ctypes.POINTER(_vp), _vp, _vp, _vp,
                                              ctypes.POINTER(_vp), _vp, _vp, ctypes.c_float, _vp, ctypes.c_size_t, _vp]),
     "colvo_debug_time_kernel": (ctypes.c_int, [ctypes.c_int, _vp, _vp]),
+    "colvo_pose_from_axisangle": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_uint32, _vp, _vp, _vp, _vp]),
+    "colvo_pose_from_axisangle_backward": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_uint32, _vp, _vp, _vp, _vp,
+                                                          _vp, _vp]),
+    "colvo_disp_to_depth": (ctypes.c_int, [ctypes.c_int32, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(_vp),
+                                           ctypes.POINTER(_vp), ctypes.c_float, ctypes.c_float, _vp]),
+    "colvo_disp_to_depth_backward": (ctypes.c_int, [ctypes.c_int32, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(_vp),
+                                                    ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.c_float,
+                                                    ctypes.c_float, _vp]),
 }
 EXPORTS = tuple(_SIGS)
 
@@ -144,13 +152,14 @@ def check(rc: int, what: str) -> None:
 
 
 def make_desc(B: int, N: int, S: int, H: int, W: int, flags: int, alpha: float = 0.85,
-              smooth_weight: float = 1e-3) -> ColvoDesc:
+              smooth_weight: float = 1e-3, geo_weight: float = 0.0) -> ColvoDesc:
     d = ColvoDesc()
     rc = load().colvo_desc_init(ctypes.byref(d), B, N, S, H, W, flags)
     if rc != 0:
         raise ValueError(f"bad problem size B={B} N={N} S={S} H={H} W={W}: {error_string(rc)}")
     d.alpha = alpha
     d.smooth_weight = smooth_weight
+    d.geo_weight = geo_weight
     return d
 
 

@@ -55,6 +55,7 @@ void fill_params(KP& P, const ColvoDesc* d) {
   }
   P.alpha = d->alpha; P.c1 = d->c1; P.c2 = d->c2; P.eps_proj = d->eps_proj; P.eps_lcc = d->eps_lcc;
   P.eps_disp = d->eps_disp; P.z_min = d->z_min; P.smooth_weight = d->smooth_weight;
+  P.geo_weight = d->geo_weight;
   P.flags = d->flags;
   P.tgt_bs = 3ll * P.HW;
   P.src_ns = 3ll * P.HW;
@@ -75,7 +76,7 @@ size_t carve_fwd(const ColvoDesc* d, void* ws, FwdBuffers& F) {
   const size_t BNS = (size_t)d->B * d->N * d->S, BS = (size_t)d->B * d->S;
   const size_t tiles = (size_t)div_up(d->W, kTileW) * div_up(d->H, kTileH);
   F.stat_chunks = stat_chunks(d);
-  F.stat_part = c.take<double>(BNS * F.stat_chunks * 5);
+  F.stat_part = c.take<double>(BNS * F.stat_chunks * kStatVals);
   F.disp_part = c.take<double>(BS * kSmoothMaxChunks);
   F.smooth_part = c.take<double>(BS * kSmoothMaxChunks * 3);
   F.loss_part = c.take<double>((size_t)d->B * tiles);
@@ -147,7 +148,7 @@ int colvo_desc_init(ColvoDesc* d, int32_t B, int32_t N, int32_t S, int32_t H, in
   d->B = B; d->N = N; d->S = S; d->H = H; d->W = W;
   for (int k = 0; k < COLVO_MAX_SCALES && k < S; ++k) { d->h[k] = H >> k; d->w[k] = W >> k; }
   d->alpha = 0.85f; d->c1 = 1e-4f; d->c2 = 9e-4f; d->eps_proj = 1e-7f; d->eps_lcc = 1e-6f; d->eps_disp = 1e-7f;
-  d->z_min = 1e-3f; d->smooth_weight = 1e-3f;
+  d->z_min = 1e-3f; d->smooth_weight = 1e-3f; d->geo_weight = 0.f;
   d->flags = flags;
   return check_desc(d);
 }
@@ -173,8 +174,8 @@ int colvo_saved_doubles(const ColvoDesc* d, size_t* count) {
 }
 
 int colvo_photo_forward(const ColvoDesc* d, const float* tgt, const float* srcs, const float* const* depth,
-                        const float* K, const float* T, float* loss, float* ab, uint8_t* valid, uint8_t* sel,
-                        double* saved, void* ws, size_t ws_bytes, void* stream) {
+                        const float* K, const float* T, const float* src_depth, float* loss, float* ab,
+                        uint8_t* valid, uint8_t* sel, double* saved, void* ws, size_t ws_bytes, void* stream) {
   int rc = check_desc(d);
   if (rc) return rc;
   if (!tgt || !srcs || !depth || !K || !T || !loss || !ab || !ws) return COLVO_E_NULL_PTR;
@@ -187,6 +188,7 @@ int colvo_photo_forward(const ColvoDesc* d, const float* tgt, const float* srcs,
   KP P;
   fill_params(P, d);
   P.tgt = tgt; P.srcs = srcs; P.K = K; P.T = T;
+  P.src_depth = (d->geo_weight != 0.f) ? src_depth : nullptr;
   for (int k = 0; k < d->S; ++k) P.depth[k] = depth[k];
   SavedView sv;
   carve_saved(d, (d->flags & COLVO_F_SAVE_FOR_BWD) ? saved : nullptr, sv);
@@ -194,9 +196,9 @@ int colvo_photo_forward(const ColvoDesc* d, const float* tgt, const float* srcs,
 }
 
 int colvo_photo_backward(const ColvoDesc* d, const float* tgt, const float* srcs, const float* const* depth,
-                         const float* K, const float* T, const float* grad_loss, const uint8_t* sel,
-                         const double* saved, float* const* grad_depth, float* grad_T, float* grad_srcs, void* ws,
-                         size_t ws_bytes, void* stream) {
+                         const float* K, const float* T, const float* src_depth, const float* grad_loss,
+                         const uint8_t* sel, const double* saved, float* const* grad_depth, float* grad_T,
+                         float* grad_srcs, float* grad_src_depth, void* ws, size_t ws_bytes, void* stream) {
   int rc = check_desc(d);
   if (rc) return rc;
   if (!tgt || !srcs || !depth || !K || !T || !grad_loss || !sel || !saved || !grad_depth || !grad_T || !ws)
@@ -211,11 +213,12 @@ int colvo_photo_backward(const ColvoDesc* d, const float* tgt, const float* srcs
   KP P;
   fill_params(P, d);
   P.tgt = tgt; P.srcs = srcs; P.K = K; P.T = T;
+  P.src_depth = (d->geo_weight != 0.f) ? src_depth : nullptr;
   for (int k = 0; k < d->S; ++k) P.depth[k] = depth[k];
   SavedView sv;
   carve_saved(d, const_cast<double*>(saved), sv);
   return (int)launch_backward(P, Bw, grad_loss, sel, sv, grad_depth, grad_T, want_src ? grad_srcs : nullptr,
-                              static_cast<cudaStream_t>(stream));
+                              P.src_depth ? grad_src_depth : nullptr, static_cast<cudaStream_t>(stream));
 }
 
 int colvo_debug_time_kernel(int which, void* ev_start, void* ev_stop) {
@@ -234,7 +237,7 @@ static size_t carve_consistency(int F, int H, int W, void* ws, double** stat, in
   const size_t Pn = (size_t)(F - 1);
   const size_t tiles = (size_t)div_up(W, kTileW) * div_up(H, kTileH);
   *chunks = div_up(H * W, kThreads * kStatPPT);
-  *stat = c.take<double>(Pn * (*chunks) * 5);
+  *stat = c.take<double>(Pn * (*chunks) * kStatVals);
   *pe_part = c.take<double>(Pn * tiles * 2);
   *ab = c.take<float>(Pn * 2);
   return c.off;
@@ -355,11 +358,12 @@ int colvo_photo_step_host(const ColvoDesc* d_in, const float* h_tgt, const float
   k_fill_scalar<<<1, 1, 0, st>>>(A.one, grad_scale);
   const float* depth_p[kMaxS] = {A.depth[0], A.depth[1], A.depth[2], A.depth[3]};
   float* gdepth_p[kMaxS] = {A.grad_depth[0], A.grad_depth[1], A.grad_depth[2], A.grad_depth[3]};
-  rc = colvo_photo_forward(&d, A.tgt, A.srcs, depth_p, A.K, A.T, A.loss, A.ab, nullptr, A.sel, A.saved, A.ws,
+  d.geo_weight = 0.f;   // the host step carries no source depth maps
+  rc = colvo_photo_forward(&d, A.tgt, A.srcs, depth_p, A.K, A.T, nullptr, A.loss, A.ab, nullptr, A.sel, A.saved, A.ws,
                            A.ws_bytes, stream);
   if (rc) return rc;
-  rc = colvo_photo_backward(&d, A.tgt, A.srcs, depth_p, A.K, A.T, A.one, A.sel, A.saved, gdepth_p, A.grad_T,
-                            want_src ? A.grad_srcs : nullptr, A.ws, A.ws_bytes, stream);
+  rc = colvo_photo_backward(&d, A.tgt, A.srcs, depth_p, A.K, A.T, nullptr, A.one, A.sel, A.saved, gdepth_p, A.grad_T,
+                            want_src ? A.grad_srcs : nullptr, nullptr, A.ws, A.ws_bytes, stream);
   if (rc) return rc;
   CV_COPY(h_loss, A.loss, 1, cudaMemcpyDeviceToHost);
   for (int k = 0; k < d.S; ++k) CV_COPY(h_grad_depth[k], A.grad_depth[k], B * d.h[k] * d.w[k], cudaMemcpyDeviceToHost);

@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_BWD)
                 const double* __restrict__ saved_frame, const double* __restrict__ saved_scale,
                 const float* __restrict__ s_field0, const float* __restrict__ coef_in, float* __restrict__ grad_d0,
                 float* __restrict__ dD1, float* __restrict__ dD2, float* __restrict__ dD3,
-                float* __restrict__ grad_srcs, double* __restrict__ pose_part) {
+                float* __restrict__ grad_srcs, float* __restrict__ grad_src_depth, double* __restrict__ pose_part) {
   // dynamic shared memory, carved by hand
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4 (*coef)[kCN * 3] = reinterpret_cast<float4 (*)[kCN * 3]>(smem_raw);   // [2]: (ca, cb, cg, -) per window
@@ -204,10 +204,30 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_BWD)
             g00 += P.HW; g01 += P.HW; g10 += P.HW; g11 += P.HW;
           }
         }
+        // geometric consistency (f-2): gradient to Z' directly, to the sampled source depth (scatter) and,
+        // through its spatial derivative, to (u', v')
+        float dZp_direct = 0.f;
+        if (P.src_depth && g.valid) {
+          float d4[4], dZ, dS;
+          const float ds = sample_plane(P.src_depth + (long long)(b * P.N + n) * P.HW, t, P.W, d4);
+          geo_diff(g.Zp, ds, dZ, dS);
+          const float wg = go * P.geo_weight / ((float)P.S * (float)P.B * (float)P.N * (float)P.HW);
+          dZp_direct = wg * dZ;
+          const float gS = wg * dS;
+          du += gS * ((1.f - t.wy) * (d4[1] - d4[0]) + t.wy * (d4[3] - d4[2]));
+          dv += gS * ((1.f - t.wx) * (d4[2] - d4[0]) + t.wx * (d4[3] - d4[1]));
+          if (grad_src_depth) {
+            float* gd = grad_src_depth + (long long)(b * P.N + n) * P.HW;
+            atomicAdd(gd + (t.y0 * P.W + t.x0), w00 * gS);
+            atomicAdd(gd + (t.y0 * P.W + t.x1), w01 * gS);
+            atomicAdd(gd + (t.y1 * P.W + t.x0), w10 * gS);
+            atomicAdd(gd + (t.y1 * P.W + t.x1), w11 * gS);
+          }
+        }
         if (!t.gx) du = 0.f;
         if (!t.gy) dv = 0.f;
         float dXp[3];
-        dD += project_adjoint(g, cam, pose, du, dv, dXp);
+        dD += project_adjoint(g, cam, pose, du, dv, dZp_direct, dXp);
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
           pw[n][i] = fmaf(dXp[i], D_own, pw[n][i]);
@@ -364,8 +384,12 @@ static size_t photo_bwd_smem() {
 
 cudaError_t launch_backward(const KP& P, const BwdBuffers& Wk, const float* grad_loss, const uint8_t* sel,
                             const SavedView& sv, float* const* grad_depth, float* grad_T, float* grad_srcs,
-                            cudaStream_t st) {
+                            float* grad_src_depth, cudaStream_t st) {
   cudaError_t e;
+  if (grad_src_depth) {
+    e = cudaMemsetAsync(grad_src_depth, 0, sizeof(float) * (size_t)P.B * P.N * P.HW, st);
+    if (e != cudaSuccess) return e;
+  }
   if (grad_srcs) {
     e = cudaMemsetAsync(grad_srcs, 0, sizeof(float) * (size_t)P.B * P.N * 3 * P.HW, st);
     if (e != cudaSuccess) return e;
@@ -378,10 +402,12 @@ cudaError_t launch_backward(const KP& P, const BwdBuffers& Wk, const float* grad
     cudaFuncSetAttribute(k_photo_bwd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)photo_bwd_smem<2>());
     if (P.N == 1)
       k_photo_bwd<1><<<grid, kThreads, photo_bwd_smem<1>(), st>>>(P, grad_loss, sel, sv.frame, sv.scale, sv.s_field[0], sv.coef, grad_depth[0],
-                                                Wk.dDhat[1], Wk.dDhat[2], Wk.dDhat[3], grad_srcs, Wk.pose_part);
+                                                Wk.dDhat[1], Wk.dDhat[2], Wk.dDhat[3], grad_srcs, grad_src_depth,
+                                                                      Wk.pose_part);
     else
       k_photo_bwd<2><<<grid, kThreads, photo_bwd_smem<2>(), st>>>(P, grad_loss, sel, sv.frame, sv.scale, sv.s_field[0], sv.coef, grad_depth[0],
-                                                Wk.dDhat[1], Wk.dDhat[2], Wk.dDhat[3], grad_srcs, Wk.pose_part);
+                                                Wk.dDhat[1], Wk.dDhat[2], Wk.dDhat[3], grad_srcs, grad_src_depth,
+                                                                      Wk.pose_part);
   }
   k_pose_final<<<P.B * P.N, kThreads, 0, st>>>(P, Wk.pose_part, grad_T);
   if (P.S > 1) {

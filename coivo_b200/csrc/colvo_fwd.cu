@@ -94,7 +94,8 @@ __global__ void __launch_bounds__(kThreads)
 template <int NS>
 __global__ void __launch_bounds__(kThreads, COLVO_MINB_STATS)
     k_warp_stats(KP P, double* __restrict__ part, uint8_t* __restrict__ valid_out, float* __restrict__ iw_out) {
-  __shared__ double sm[(kThreads / 32) * 5 * NS];
+  constexpr int NV = kStatVals * NS;
+  __shared__ double sm[(kThreads / 32) * NV];
   const int bk = blockIdx.y, k = bk % P.S, b = bk / P.S;
   const Cam cam = load_cam(P, b);
   const float* Dk = P.depth[k] + (long long)b * P.depth_bs[k];
@@ -104,9 +105,9 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_STATS)
   for (int n = 0; n < NS; ++n) pose[n] = load_pose(P, b, n);
   int pix = blockIdx.x * (kThreads * kStatPPT) + threadIdx.x;
   int py = pix / P.W, px = pix - py * P.W;
-  double acc[5 * NS];
+  double acc[NV];
 #pragma unroll
-  for (int i = 0; i < 5 * NS; ++i) acc[i] = 0.0;
+  for (int i = 0; i < NV; ++i) acc[i] = 0.0;
 #pragma unroll 2
   for (int i = 0; i < kStatPPT; ++i) {
     if (pix < P.HW) {
@@ -127,11 +128,16 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_STATS)
           o[2 * (long long)P.HW] = x[2];
         }
         if (g.valid) {
-          acc[5 * n + 0] += 3.0;
-          acc[5 * n + 1] += (double)(x[0] + x[1] + x[2]);
-          acc[5 * n + 2] += (double)(y0 + y1 + y2);
-          acc[5 * n + 3] += (double)(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
-          acc[5 * n + 4] += (double)(x[0] * y0 + x[1] * y1 + x[2] * y2);
+          acc[kStatVals * n + 0] += 3.0;
+          acc[kStatVals * n + 1] += (double)(x[0] + x[1] + x[2]);
+          acc[kStatVals * n + 2] += (double)(y0 + y1 + y2);
+          acc[kStatVals * n + 3] += (double)(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+          acc[kStatVals * n + 4] += (double)(x[0] * y0 + x[1] * y1 + x[2] * y2);
+          if (P.src_depth) {       // geometric consistency (f-2): per-pixel, so it lives in this pass
+            float d4[4], dZ, dS;
+            const float ds = sample_plane(P.src_depth + (long long)(b * P.N + n) * P.HW, t, P.W, d4);
+            acc[kStatVals * n + 5] += (double)geo_diff(g.Zp, ds, dZ, dS);
+          }
         }
       }
     }
@@ -141,18 +147,18 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_STATS)
   }
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
-  for (int i = 0; i < 5 * NS; ++i) {
+  for (int i = 0; i < NV; ++i) {
     double s = warp_sum(acc[i]);
-    if (lane == 0) sm[wid * 5 * NS + i] = s;
+    if (lane == 0) sm[wid * NV + i] = s;
   }
   __syncthreads();
-  if (threadIdx.x < 5 * NS) {
+  if (threadIdx.x < NV) {
     double s = 0.0;
 #pragma unroll
-    for (int w = 0; w < kThreads / 32; ++w) s += sm[w * 5 * NS + threadIdx.x];
-    const int n = threadIdx.x / 5, j = threadIdx.x - 5 * n;
+    for (int w = 0; w < kThreads / 32; ++w) s += sm[w * NV + threadIdx.x];
+    const int n = threadIdx.x / kStatVals, j = threadIdx.x - kStatVals * n;
     const int bnk = (b * P.N + n) * P.S + k;
-    part[((long long)bnk * gridDim.x + blockIdx.x) * 5 + j] = s;
+    part[((long long)bnk * gridDim.x + blockIdx.x) * kStatVals + j] = s;
   }
 }
 
@@ -164,7 +170,7 @@ __global__ void __launch_bounds__(32)
   if (P.flags & 1u) {
     for (int c = lane; c < chunks; c += 32) {
 #pragma unroll
-      for (int j = 0; j < 5; ++j) s[j] += part[((long long)bnk * chunks + c) * 5 + j];
+      for (int j = 0; j < 5; ++j) s[j] += part[((long long)bnk * chunks + c) * kStatVals + j];
     }
 #pragma unroll
     for (int j = 0; j < 5; ++j) s[j] = warp_sum(s[j]);
@@ -512,8 +518,9 @@ __global__ void __launch_bounds__(kThreads)
 // blocks [1+BNS, 1+BNS+B*S): sum_p s_p d_p of (b, k) for the smoothness adjoint.
 __global__ void __launch_bounds__(kThreads)
     k_finalize_fwd(KP P, const double* __restrict__ loss_part, const double* __restrict__ g_part,
-                   const double* __restrict__ smooth_part, float* __restrict__ loss, double* __restrict__ saved_frame,
-                   double* __restrict__ saved_scale, int need_g) {
+                   const double* __restrict__ smooth_part, const double* __restrict__ stat_part, int stat_chunks,
+                   float* __restrict__ loss, double* __restrict__ saved_frame, double* __restrict__ saved_scale,
+                   int need_g) {
   __shared__ double sm[(kThreads / 32) * 2];
   __shared__ double wk_s[kMaxS][2];
   const int tiles = P.tiles_x * P.tiles_y;
@@ -533,8 +540,12 @@ __global__ void __launch_bounds__(kThreads)
       wk_s[k][1] = wy;
     }
     __syncthreads();
-    double acc[2] = {0.0, 0.0};                       // photometric sum, weighted smoothness sum
+    double acc[2] = {0.0, 0.0};                       // photometric sum, weighted smoothness (+ geometric) sum
     for (int i = threadIdx.x; i < P.B * tiles; i += kThreads) acc[0] += loss_part[i];
+    if (P.src_depth) {                                // L_geo,k = sum of diffs / (B N HW), weight geo_weight
+      const double wg = (double)P.geo_weight / ((double)P.B * (double)P.N * (double)P.HW);
+      for (int i = threadIdx.x; i < BNS * stat_chunks; i += kThreads) acc[1] += stat_part[(long long)i * kStatVals + 5] * wg;
+    }
     for (int i = threadIdx.x; i < P.B * P.S * kSmoothMaxChunks; i += kThreads) {
       const int bk = i / kSmoothMaxChunks, c = i - bk * kSmoothMaxChunks, k = bk % P.S;
       if (c < P.sm_chunks[k])
@@ -700,8 +711,8 @@ cudaError_t launch_forward(const KP& P, const FwdBuffers& Wk, float* loss, float
     k_smooth_fwd<false><<<chunks, kThreads, 0, st>>>(P, Wk.disp_part, Wk.pyr[1], Wk.pyr[2], Wk.pyr[3], Wk.smooth_part,
                                                      nullptr, nullptr, nullptr, nullptr, nullptr);
   const int nfin = 1 + (save ? BNS + P.B * P.S : 0);
-  k_finalize_fwd<<<nfin, kThreads, 0, st>>>(P, Wk.loss_part, Wk.g_part, Wk.smooth_part, loss, sv.frame, sv.scale,
-                                            need_g);
+  k_finalize_fwd<<<nfin, kThreads, 0, st>>>(P, Wk.loss_part, Wk.g_part, Wk.smooth_part, Wk.stat_part, Wk.stat_chunks,
+                                            loss, sv.frame, sv.scale, need_g);
   return cudaGetLastError();
 }
 

@@ -13,6 +13,7 @@ constexpr int kThreads = 256;
 constexpr int kTileW = 32;       // one warp = one tile row: coalesced 128 B rows
 constexpr int kTileH = 8;
 constexpr int kStatPPT = 8;      // pixels per thread in the LCC statistics pass
+constexpr int kStatVals = 6;     // per (frame, chunk): n, Sx, Sy, Sxx, Sxy, sum of geometric-consistency diffs
 constexpr int kSmoothMaxChunks = 64;
 constexpr int kSmoothPixPerBlock = 1024;
 
@@ -37,6 +38,8 @@ struct KP {
   const float* depth[kMaxS];         // [B,1,h_k,w_k]
   const float* K;                    // [B,3,3]
   const float* T;                    // [B,N,4,4]
+  const float* src_depth;            // [B,N,1,H,W] or null: geometric-consistency term (f-2)
+  float geo_weight;
   long long tgt_bs, src_bs, src_ns;  // element strides (the consistency sweep aliases one frame array)
   long long depth_bs[kMaxS];
   int K_bs, T_bs, T_ns;
@@ -120,6 +123,16 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool pr
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
+// bilinear sample of one extra plane (the source depth map) with the taps of a warped pixel
+__device__ __forceinline__ float sample_plane(const float* __restrict__ plane, const Taps& t, int W, float (&d)[4]) {
+  const int r0 = t.y0 * W, r1 = t.y1 * W;
+  d[0] = __ldg(plane + (r0 + t.x0));
+  d[1] = __ldg(plane + (r0 + t.x1));
+  d[2] = __ldg(plane + (r1 + t.x0));
+  d[3] = __ldg(plane + (r1 + t.x1));
+  return bilerp(d[0], d[1], d[2], d[3], t.wx, t.wy);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -177,7 +190,7 @@ __device__ __forceinline__ void block_sum_slots(const float* slots, double* part
 
 // ---- launchers implemented in colvo_fwd.cu / colvo_bwd.cu (called by colvo_api.cu) ----
 struct FwdBuffers {
-  double* stat_part;     // [B*N*S][stat_chunks][5]
+  double* stat_part;     // [B*N*S][stat_chunks][kStatVals]
   int stat_chunks;
   float* pyr[kMaxS];     // target pyramid, k >= 1: [B,3,h_k,w_k]
   double* disp_part;     // [B*S][kSmoothMaxChunks]
@@ -215,7 +228,7 @@ cudaError_t launch_forward(const KP& P, const FwdBuffers& W, float* loss, float*
                            const SavedView& saved, cudaStream_t st);
 cudaError_t launch_backward(const KP& P, const BwdBuffers& W, const float* grad_loss, const uint8_t* sel,
                             const SavedView& saved, float* const* grad_depth, float* grad_T, float* grad_srcs,
-                            cudaStream_t st);
+                            float* grad_src_depth, cudaStream_t st);
 cudaError_t launch_consistency(const KP& P, double* stat_part, int stat_chunks, double* pe_part, float* ab,
                                float* out, cudaStream_t st);
 

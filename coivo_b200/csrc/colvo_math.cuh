@@ -78,6 +78,7 @@ struct Geo {
   float X, Y, Z;     // back-projected point in the target camera (Z = depth)
   float rx, ry;      // ray
   float iz;          // 1 / (Z' + eps)
+  float Zp;          // depth of the transformed point in the source camera
   bool valid;
 };
 // the ray of a pixel depends on the pixel and K only: kernels hoist it out of their (k, n) loops
@@ -95,6 +96,7 @@ CV_HD Geo reproject_ray(float rx, float ry, float D, const Cam& c, const Pose& p
   float Zp = p_add(p_add(p_add(p_mul(p.r[6], g.X), p_mul(p.r[7], g.Y)), p_mul(p.r[8], g.Z)), p.t[2]);
   float x = p_add(p_mul(c.fx, Xp), p_mul(c.cx, Zp));
   float y = p_add(p_mul(c.fy, Yp), p_mul(c.cy, Zp));
+  g.Zp = Zp;
   g.iz = p_rcp(p_add(Zp, eps));
   g.u = p_mul(x, g.iz);
   g.v = p_mul(y, g.iz);
@@ -224,16 +226,32 @@ CV_HD float reflect_mult(int q, int p, int n) {
   return m;
 }
 
+// ---- geometric consistency  diff = clamp(|Z' - Ds| / (Z' + Ds), 0, 1)  (oracle A16) ----
+// returns diff and its partial derivatives (torch semantics: abs' = sign with sign(0) = 0, clamp passes
+// the gradient on the closed interval)
+CV_HD float geo_diff(float Zp, float ds, float& dZ, float& dS) {
+  const float num = Zp - ds, den = Zp + ds;
+  const float iden = 1.0f / den;
+  const float r = fabsf(num) * iden;
+  const bool pass = (r >= 0.f) && (r <= 1.f);
+  const float sg = sgn(num);
+  dZ = pass ? (sg - r) * iden : 0.f;      // d/dZ' [ |n| / d ] = sg/d - |n|/d^2
+  dS = pass ? (-sg - r) * iden : 0.f;
+  return clamp01(r);
+}
+
 // ---- row 11: adjoint of projection / transform / back-projection for one pixel ----
 // in: du, dv = dL/du', dL/dv'.  out: dD = dL/dDhat and dXp[3] = dL/dX' (gradient w.r.t. the
 // transformed point).  The pose gradient follows from dXp alone:
 //   dL/dt_i = sum dXp_i,   dL/dR_ij = sum dXp_i * X_j   with X = D * (rx, ry, 1)
 // so a kernel only has to accumulate dXp_i and dXp_i * D per pixel (the ray is constant per pixel).
-CV_HD float project_adjoint(const Geo& g, const Cam& c, const Pose& p, float du, float dv, float (&dXp)[3]) {
+// dZp_direct: gradient that reaches Z' directly (the geometric-consistency term), 0 otherwise.
+CV_HD float project_adjoint(const Geo& g, const Cam& c, const Pose& p, float du, float dv, float dZp_direct,
+                            float (&dXp)[3]) {
   float dx = du * g.iz, dy = dv * g.iz;
   dXp[0] = c.fx * dx;
   dXp[1] = c.fy * dy;
-  dXp[2] = c.cx * dx + c.cy * dy - g.iz * (du * g.u + dv * g.v);
+  dXp[2] = c.cx * dx + c.cy * dy - g.iz * (du * g.u + dv * g.v) + dZp_direct;
   float dX = p.r[0] * dXp[0] + p.r[3] * dXp[1] + p.r[6] * dXp[2];
   float dY = p.r[1] * dXp[0] + p.r[4] * dXp[1] + p.r[7] * dXp[2];
   float dZ = p.r[2] * dXp[0] + p.r[5] * dXp[1] + p.r[8] * dXp[2];

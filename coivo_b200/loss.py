@@ -74,15 +74,24 @@ class _Workspace:
 
 class _PhotoLossFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, pose, K, tgt, srcs, alpha, smooth_weight, lcc, lcc_detach, want_valid, *depth):
+    def forward(ctx, pose, K, tgt, srcs, alpha, smooth_weight, lcc, lcc_detach, want_valid, src_depth, geo_weight, *depth):
         B, N, S, H, W = _check_inputs(depth, pose, K, tgt, srcs)
+        if src_depth is not None:
+            if tuple(src_depth.shape) != (B, N, 1, H, W):
+                raise ValueError("src_depth must be [B,N,1,H,W]")
+            if src_depth.dtype != torch.float32:
+                raise TypeError("src_depth must be float32")
+            if src_depth.device != tgt.device or not src_depth.is_contiguous():
+                raise ValueError("src_depth must be a contiguous tensor on the inputs' device")
+        else:
+            geo_weight = 0.0
         lib = _lib.load()
         dev = tgt.device
-        needs_grad = any(ctx.needs_input_grad[i] for i in (0, 3)) or any(ctx.needs_input_grad[9:])
+        needs_grad = any(ctx.needs_input_grad[i] for i in (0, 3, 9)) or any(ctx.needs_input_grad[11:])
         flags = (_lib.F_LCC if lcc else 0) | (_lib.F_LCC_DETACH if lcc_detach else 0)
         if needs_grad:
             flags |= _lib.F_SAVE_FOR_BWD
-        desc = _lib.make_desc(B, N, S, H, W, flags, alpha, smooth_weight)
+        desc = _lib.make_desc(B, N, S, H, W, flags, alpha, smooth_weight, geo_weight)
         nbytes = ctypes.c_size_t()
         _lib.check(lib.colvo_workspace_bytes(ctypes.byref(desc), ctypes.byref(nbytes)), "colvo_workspace_bytes")
         nsaved = ctypes.c_size_t()
@@ -97,14 +106,16 @@ class _PhotoLossFn(torch.autograd.Function):
             stream = torch.cuda.current_stream(dev).cuda_stream
             rc = lib.colvo_photo_forward(
                 ctypes.byref(desc), tgt.data_ptr(), srcs.data_ptr(), _lib.ptr_array([d.data_ptr() for d in depth]),
-                K.data_ptr(), pose.data_ptr(), loss.data_ptr(), ab.data_ptr(),
-                valid.data_ptr() if valid is not None else None, sel.data_ptr(), saved.data_ptr(), ws.data_ptr(),
-                ws.numel(), stream)
+                K.data_ptr(), pose.data_ptr(), src_depth.data_ptr() if src_depth is not None else None, loss.data_ptr(),
+                ab.data_ptr(), valid.data_ptr() if valid is not None else None, sel.data_ptr(), saved.data_ptr(),
+                ws.data_ptr(), ws.numel(), stream)
         _lib.check(rc, "colvo_photo_forward")
-        ctx.desc_args = (B, N, S, H, W, flags, alpha, smooth_weight)
+        ctx.desc_args = (B, N, S, H, W, flags, alpha, smooth_weight, geo_weight)
         ctx.n_depth = S
+        ctx.has_src_depth = src_depth is not None
         if needs_grad:
-            ctx.save_for_backward(pose, K, tgt, srcs, sel, saved, *depth)
+            extra = (src_depth,) if src_depth is not None else ()
+            ctx.save_for_backward(pose, K, tgt, srcs, sel, saved, *extra, *depth)
         ctx.mark_non_differentiable(ab, sel)
         if valid is not None:
             ctx.mark_non_differentiable(valid)
@@ -114,14 +125,15 @@ class _PhotoLossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_loss, *unused):
         pose, K, tgt, srcs, sel, saved = ctx.saved_tensors[:6]
-        depth = ctx.saved_tensors[6:]
-        B, N, S, H, W, flags, alpha, smooth_weight = ctx.desc_args
+        src_depth = ctx.saved_tensors[6] if ctx.has_src_depth else None
+        depth = ctx.saved_tensors[7:] if ctx.has_src_depth else ctx.saved_tensors[6:]
+        B, N, S, H, W, flags, alpha, smooth_weight, geo_weight = ctx.desc_args
         want_src = ctx.needs_input_grad[3]
         if not want_src:
             flags |= _lib.F_NO_SRC_GRAD
         lib = _lib.load()
         dev = tgt.device
-        desc = _lib.make_desc(B, N, S, H, W, flags, alpha, smooth_weight)
+        desc = _lib.make_desc(B, N, S, H, W, flags, alpha, smooth_weight, geo_weight)
         nbytes = ctypes.c_size_t()
         _lib.check(lib.colvo_workspace_bytes(ctypes.byref(desc), ctypes.byref(nbytes)), "colvo_workspace_bytes")
         with torch.cuda.device(dev):
@@ -130,15 +142,19 @@ class _PhotoLossFn(torch.autograd.Function):
             grad_depth = [torch.empty_like(d) for d in depth]
             grad_T = torch.empty_like(pose)
             grad_srcs = torch.empty_like(srcs) if want_src else None
+            want_sd = src_depth is not None and ctx.needs_input_grad[9]
+            grad_sd = torch.empty_like(src_depth) if want_sd else None
             stream = torch.cuda.current_stream(dev).cuda_stream
             rc = lib.colvo_photo_backward(
                 ctypes.byref(desc), tgt.data_ptr(), srcs.data_ptr(), _lib.ptr_array([d.data_ptr() for d in depth]),
-                K.data_ptr(), pose.data_ptr(), go.data_ptr(), sel.data_ptr(), saved.data_ptr(),
-                _lib.ptr_array([g.data_ptr() for g in grad_depth]), grad_T.data_ptr(),
-                grad_srcs.data_ptr() if want_src else None, ws.data_ptr(), ws.numel(), stream)
+                K.data_ptr(), pose.data_ptr(), src_depth.data_ptr() if src_depth is not None else None, go.data_ptr(),
+                sel.data_ptr(), saved.data_ptr(), _lib.ptr_array([g.data_ptr() for g in grad_depth]), grad_T.data_ptr(),
+                grad_srcs.data_ptr() if want_src else None, grad_sd.data_ptr() if want_sd else None, ws.data_ptr(),
+                ws.numel(), stream)
         _lib.check(rc, "colvo_photo_backward")
-        gd = [g if ctx.needs_input_grad[9 + i] else None for i, g in enumerate(grad_depth)]
-        return (grad_T if ctx.needs_input_grad[0] else None, None, None, grad_srcs, None, None, None, None, None, *gd)
+        gd = [g if ctx.needs_input_grad[11 + i] else None for i, g in enumerate(grad_depth)]
+        return (grad_T if ctx.needs_input_grad[0] else None, None, None, grad_srcs, None, None, None, None, None,
+                grad_sd, None, *gd)
 
 
 def photometric_loss(
@@ -153,6 +169,8 @@ def photometric_loss(
     lcc: bool = True,
     lcc_detach: bool = False,
     return_masks: bool = False,
+    src_depth: Optional[torch.Tensor] = None,
+    geo_weight: float = 0.0,
 ):
     """View-synthesis photometric loss with LCC, min-reprojection / auto-mask and edge-aware
     smoothness over S scales and N neighbouring frames.
@@ -161,10 +179,13 @@ def photometric_loss(
     tgt `[B,3,H,W]`; srcs `[B,N,3,H,W]`.  All CUDA, fp32, contiguous.  Differentiable in
     depth, pose and srcs; K and tgt get no gradient (oracle A14).
 
+    `src_depth [B,N,1,H,W]` (the depth maps of the source frames) with `geo_weight > 0` adds the
+    geometric-consistency term of SURVEY.md section 8(f)-2 (oracle A16); it is differentiable too.
+
     Returns the 0-dim loss, or `(loss, valid u8 [B,N,S,H,W], sel u8 [B,S,H,W], ab [B,N,S,2])`.
     """
     out = _PhotoLossFn.apply(pose, K, tgt, srcs, float(alpha), float(smooth_weight), bool(lcc), bool(lcc_detach),
-                             bool(return_masks), *depth)
+                             bool(return_masks), src_depth, float(geo_weight), *depth)
     if return_masks:
         loss, ab, sel, valid = out
         return loss, valid, sel, ab

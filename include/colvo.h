@@ -59,6 +59,7 @@ typedef struct ColvoDesc {
   float eps_disp;                  /* 1e-7 on the mean inverse depth                             */
   float z_min;                     /* 1e-3                                                       */
   float smooth_weight;             /* 1e-3 (scaled by 2^-k per scale)                            */
+  float geo_weight;                /* weight of the geometric-consistency term (needs src_depth) */
   uint32_t flags;
 } ColvoDesc;
 
@@ -75,6 +76,8 @@ int colvo_saved_doubles(const ColvoDesc* d, size_t* count);
 
 /* Forward: SURVEY.md section 8(a) rows 0-10.
  *   tgt [B,3,H,W]  srcs [B,N,3,H,W]  depth[k] [B,1,h_k,w_k]  K [B,3,3]  T [B,N,4,4]
+ *   src_depth [B,N,1,H,W]     (nullable) depth maps of the source frames: with geo_weight != 0 adds the
+ *                             geometric-consistency term (README.md:1,7)
  *   loss  [1]                 (out)
  *   ab    [B,N,S,2]           (out)  LCC gain/bias per warped frame and scale
  *   valid [B,N,S,H,W] u8      (out, nullable)  bit-exact projection validity
@@ -82,20 +85,21 @@ int colvo_saved_doubles(const ColvoDesc* d, size_t* count);
  *   saved [colvo_saved_doubles] (out; required with COLVO_F_SAVE_FOR_BWD, else nullable)
  */
 int colvo_photo_forward(const ColvoDesc* d, const float* tgt, const float* srcs, const float* const* depth,
-                        const float* K, const float* T, float* loss, float* ab, uint8_t* valid, uint8_t* sel,
-                        double* saved, void* ws, size_t ws_bytes, void* stream);
+                        const float* K, const float* T, const float* src_depth, float* loss, float* ab,
+                        uint8_t* valid, uint8_t* sel, double* saved, void* ws, size_t ws_bytes, void* stream);
 
 /* Backward: SURVEY.md section 8(a) row 11.  Inputs as in the forward plus its sel / saved.
  *   grad_loss  [1] device scalar (dL_total / dloss)
  *   grad_depth[k] [B,1,h_k,w_k]   (out, overwritten)
  *   grad_T     [B,N,4,4]          (out, overwritten; bottom row 0)
  *   grad_srcs  [B,N,3,H,W]        (out, overwritten; nullable with COLVO_F_NO_SRC_GRAD)
+ *   grad_src_depth [B,N,1,H,W]    (out, overwritten; nullable)
  * No gradient is produced for K or tgt (oracle A14).
  */
 int colvo_photo_backward(const ColvoDesc* d, const float* tgt, const float* srcs, const float* const* depth,
-                         const float* K, const float* T, const float* grad_loss, const uint8_t* sel,
-                         const double* saved, float* const* grad_depth, float* grad_T, float* grad_srcs, void* ws,
-                         size_t ws_bytes, void* stream);
+                         const float* K, const float* T, const float* src_depth, const float* grad_loss,
+                         const uint8_t* sel, const double* saved, float* const* grad_depth, float* grad_T,
+                         float* grad_srcs, float* grad_src_depth, void* ws, size_t ws_bytes, void* stream);
 
 /* Inference-time warp + LCC consistency sweep over a frame sequence (BASELINE config 5;
  * README.md:29: depth maps are stitched along the trajectory -- this is the check that gates it).
@@ -121,6 +125,24 @@ int colvo_photo_step_host(const ColvoDesc* d, const float* h_tgt, const float* h
                           const float* h_K, const float* h_T, float* h_loss, float* const* h_grad_depth,
                           float* h_grad_T, float* h_grad_srcs, float grad_scale, void* arena, size_t arena_bytes,
                           void* stream);
+
+/* Front-end: raw network outputs -> the tensors the loss takes.
+ * Monodepth2's transformation_from_parameters / disp_to_depth (oracle/frontend.py).
+ *   axisangle, translation [B,N,3]; bit n of invert_mask: source n's motion is given source->target and
+ *   must be inverted (the frame t-1 convention); T, grad_T [B,N,4,4].
+ *   disp_to_depth: depth = 1 / (1/max_depth + (1/min_depth - 1/max_depth) * disp), S tensors of counts[k]
+ *   elements each (counts is a HOST array); the backward takes the forward's depth.
+ */
+int colvo_pose_from_axisangle(int32_t B, int32_t N, uint32_t invert_mask, const float* axisangle,
+                              const float* translation, float* T, void* stream);
+int colvo_pose_from_axisangle_backward(int32_t B, int32_t N, uint32_t invert_mask, const float* axisangle,
+                                       const float* translation, const float* grad_T, float* grad_axisangle,
+                                       float* grad_translation, void* stream);
+int colvo_disp_to_depth(int32_t S, const int64_t* counts, const float* const* disp, float* const* depth,
+                        float min_depth, float max_depth, void* stream);
+int colvo_disp_to_depth_backward(int32_t S, const int64_t* counts, const float* const* depth,
+                                 const float* const* grad_depth, float* const* grad_disp, float min_depth,
+                                 float max_depth, void* stream);
 
 /* Profiling aid (bench.py's roofline leg): bracket the NEXT launch of one kernel with two
  * caller-owned cudaEvent_t on the launching stream.  One-shot, process-wide; pass

@@ -6,7 +6,7 @@ weights (`/root/reference/README.md:1-31` is the whole text).  There is therefor
 reference output this file could be pinned to.  It is a plain-PyTorch CPU
 restatement of the Monodepth2-style view-synthesis loss that BASELINE.json's
 north_star names, with every assumption listed in `oracle/ASSUMPTIONS.md`
-(A0..A15).  What pins it instead: closed-form known-answer tests, fp64
+(A0..A16).  What pins it instead: closed-form known-answer tests, fp64
 `gradcheck`, and cross-checks against torch library ops (`tests/test_oracle_*.py`).
 
 Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s CPU-baseline / reference
@@ -270,6 +270,28 @@ def target_pyramid(tgt: torch.Tensor, S: int):
 
 
 # --------------------------------------------------------------------------------------
+# geometric consistency (SC-Depth style), re-using the same warp.
+# --------------------------------------------------------------------------------------
+def geometric_consistency(Zp: torch.Tensor, src_depth_n: torch.Tensor, u: torch.Tensor, v: torch.Tensor,
+                          valid: torch.Tensor) -> torch.Tensor:
+    """The title of the upstream README promises "Geometric ... Consistency" (`README.md:1`) and DCDP
+    couples depth and pose through "loss function constraints" (`README.md:7`); the formulation is the
+    SC-Depth one [A16]: the depth of the re-projected point, `Z'`, must agree with the source frame's
+    own depth map sampled where the point lands,
+
+        D_s' = bilinear_sample(D_s, u', v')            (border padding, as row 4)
+        diff = clamp(|Z' - D_s'| / (Z' + D_s'), 0, 1)
+        L_geo = mean over b, pixels of (valid ? diff : 0)
+
+    `Zp, u, v, valid [B,H,W]`, `src_depth_n [B,1,H,W]` -> scalar.  Differentiable in the target depth and
+    the pose (through Z', u', v') and in the source depth map; the mask is a constant."""
+    Ds = bilinear_sample(src_depth_n, u, v)[:, 0]
+    diff = torch.clamp((Zp - Ds).abs() / (Zp + Ds), 0, 1)
+    diff = torch.where(valid, diff, torch.zeros_like(diff))
+    return diff.mean()
+
+
+# --------------------------------------------------------------------------------------
 # Rows 8, 10: min-reprojection / auto-mask and the total.
 # --------------------------------------------------------------------------------------
 def _min_first(cands: torch.Tensor):
@@ -319,6 +341,8 @@ def photometric_loss(
     return_masks: bool = False,
     sel_override: Optional[torch.Tensor] = None,
     ab_override: Optional[torch.Tensor] = None,
+    src_depth: Optional[torch.Tensor] = None,
+    geo_weight: float = 0.0,
 ):
     """The oracle for SURVEY.md section 8(a) rows 0-10 (row 11 = autograd of this).
 
@@ -331,9 +355,15 @@ def photometric_loss(
     dependence on the warped image (straight-through), so that gradients can be
     compared against a kernel that made a different near-tie / last-ulp choice
     (SURVEY.md section 7.4 H2).
+
+    `src_depth [B,N,1,H,W]` with `geo_weight > 0` adds the geometric-consistency term of
+    SURVEY.md section 8(f)-2 (see `geometric_consistency`), per scale, with the same 1/S.
     """
     B, N, S, H, W = _validate(depth, pose, K, tgt, srcs)
     tgt_c = tgt.detach()
+    geo_on = src_depth is not None and geo_weight != 0.0
+    if geo_on and tuple(src_depth.shape) != (B, N, 1, H, W):
+        raise ValueError("src_depth must be [B,N,1,H,W]")
     # Identity candidates: raw sources, no LCC, detached (A10).
     ident = [photometric_error(srcs[:, n].detach(), tgt_c, alpha) for n in range(N)]
     pyr = target_pyramid(tgt_c, S)
@@ -343,9 +373,12 @@ def photometric_loss(
         Dhat = upsample_depth(depth[k], H, W)
         cands = list(ident)
         v_k, ab_k = [], []
+        l_geo = tgt.new_zeros(())
         for n in range(N):
-            u, v, valid, _ = reproject(Dhat, K, pose[:, n])
+            u, v, valid, Zp = reproject(Dhat, K, pose[:, n])
             Iw = bilinear_sample(srcs[:, n], u, v)
+            if geo_on:
+                l_geo = l_geo + geometric_consistency(Zp, src_depth[:, n], u, v, valid) / N
             if lcc:
                 a, b = lcc_fit(Iw.detach() if lcc_detach else Iw, tgt_c, valid)
                 if ab_override is not None:
@@ -366,7 +399,7 @@ def photometric_loss(
             m, sel = _min_first(cands)
         l_photo = m.mean()
         l_sm = smoothness(depth[k], pyr[k])
-        total = total + l_photo + (smooth_weight / (2 ** k)) * l_sm
+        total = total + l_photo + (smooth_weight / (2 ** k)) * l_sm + geo_weight * l_geo
         valids.append(torch.stack(v_k, dim=1))                # [B,N,H,W]
         sels.append(sel)
         abs_.append(torch.stack(ab_k, dim=1))                 # [B,N,2]

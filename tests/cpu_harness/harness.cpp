@@ -210,7 +210,7 @@ int harness_run(int B, int N, int S, int H, int W, unsigned flags, const float* 
             if (!t.gx) du = 0;
             if (!t.gy) dv = 0;
             float dXp[3];
-            dD[p] += project_adjoint(g, cam, pose, du, dv, dXp);
+            dD[p] += project_adjoint(g, cam, pose, du, dv, 0.f, dXp);
             float wv[3] = {dXp[0] * g.Z, dXp[1] * g.Z, dXp[2] * g.Z}, tv[3] = {dXp[0], dXp[1], dXp[2]}, e[12];
             pose_grad_expand(wv, tv, g.rx, g.ry, e);
             for (int q = 0; q < 12; ++q) gp[q] += e[q];

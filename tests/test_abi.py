@@ -68,7 +68,7 @@ def test_null_pointer_and_alignment_checks_without_touching_the_gpu():
     lib = _lib.load()
     d = _lib.make_desc(1, 2, 2, 16, 24, _lib.F_LCC)
     depth = _lib.ptr_array([None, None])
-    rc = lib.colvo_photo_forward(ctypes.byref(d), None, None, depth, None, None, None, None, None, None, None, None, 0, None)
+    rc = lib.colvo_photo_forward(ctypes.byref(d), None, None, depth, None, None, None, None, None, None, None, None, None, 0, None)
     assert rc == -3
     assert lib.colvo_debug_time_kernel(7, None, None) == -5
     assert lib.colvo_debug_time_kernel(0, None, None) == 0

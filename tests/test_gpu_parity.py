@@ -208,3 +208,35 @@ def test_graphed_step_replays_the_eager_result():
     l3 = g.replay().item()
     torch.cuda.synchronize()
     assert abs(l3 - run_cuda(d2)[0].item()) < 1e-7
+
+
+@pytest.mark.parametrize("B,H,W,N,S", [(2, 48, 64, 2, 4), (1, 37, 53, 1, 3)])
+def test_geometric_consistency_term_parity(B, H, W, N, S):
+    """the extra term, its gradients to depth / pose and to the source depth maps."""
+    d = make_triplets(B, H, W, N=N, S=S, seed=41)
+    g = torch.Generator().manual_seed(5)
+    sd = (1.0 + 0.5 * torch.rand(B, N, 1, H, W, generator=g)).contiguous()
+    depth = [x.to(DEV).requires_grad_() for x in d["depth"]]
+    pose = d["pose"].to(DEV).requires_grad_()
+    srcs = d["srcs"].to(DEV).requires_grad_()
+    sdg = sd.to(DEV).requires_grad_()
+    loss, valid, sel, ab = coivo_b200.photometric_loss(depth, pose, d["K"].to(DEV), d["tgt"].to(DEV), srcs,
+                                                       src_depth=sdg, geo_weight=0.5, return_masks=True)
+    loss.backward()
+    with torch.no_grad():
+        l_plain = coivo_b200.photometric_loss([x.detach() for x in depth], pose.detach(), d["K"].to(DEV), d["tgt"].to(DEV),
+                                              srcs.detach())
+    assert loss.item() > l_plain.item() + 1e-3            # the term is really there
+    od = [x.clone().requires_grad_() for x in d["depth"]]
+    op = d["pose"].clone().requires_grad_()
+    osr = d["srcs"].clone().requires_grad_()
+    osd = sd.clone().requires_grad_()
+    l_ref = O.photometric_loss(od, op, d["K"], d["tgt"], osr, src_depth=osd, geo_weight=0.5, sel_override=sel.cpu(),
+                               ab_override=ab.cpu())
+    l_ref.backward()
+    assert abs(loss.item() - l_ref.item()) <= TOL * abs(l_ref.item())
+    for k in range(S):
+        assert relinf(depth[k].grad, od[k].grad) < TOL, f"grad_depth[{k}]"
+    assert relinf(pose.grad[:, :, :3], op.grad[:, :, :3]) < TOL
+    assert relinf(srcs.grad, osr.grad) < TOL
+    assert relinf(sdg.grad, osd.grad) < TOL

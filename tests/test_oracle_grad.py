@@ -47,3 +47,30 @@ def test_no_grad_to_K_or_tgt():
     loss = O.photometric_loss(depth, pose, K, tgt, srcs, smooth_weight=0.0)
     g = torch.autograd.grad(loss, [tgt], allow_unused=True)
     assert g[0] is None                     # A14: tgt is detached everywhere
+
+
+def test_gradcheck_geometric_consistency_term():
+    depth, pose, K, tgt, srcs = _inputs(1, 12, 16, 2, 2, seed=3)
+    g = torch.Generator().manual_seed(0)
+    sd = (1.0 + 0.5 * torch.rand(1, 2, 1, 12, 16, generator=g, dtype=torch.float64)).requires_grad_()
+    with torch.no_grad():
+        _, _, sel, _ = O.photometric_loss(depth, pose, K, tgt, srcs, return_masks=True)
+    depth = [x.requires_grad_() for x in depth]
+    pose.requires_grad_()
+    fn = lambda d0, d1, p, s_: O.photometric_loss([d0, d1], p, K, tgt, srcs, sel_override=sel, src_depth=s_, geo_weight=0.5)
+    assert torch.autograd.gradcheck(fn, (depth[0], depth[1], pose, sd), eps=1e-6, atol=1e-6, rtol=1e-4)
+
+
+def test_geometric_consistency_is_zero_for_a_consistent_scene():
+    # fronto-parallel plane seen by a camera translated along x: Z' = D everywhere, so a source depth map equal
+    # to the same constant is perfectly consistent; a different constant gives the closed-form ratio
+    B, H, W = 1, 12, 20
+    from coivo_b200.synthetic import make_intrinsics
+    K = make_intrinsics(B, H, W)
+    T = torch.eye(4).reshape(1, 4, 4).clone()
+    T[0, 0, 3] = 0.02
+    D = torch.full((B, 1, H, W), 2.0)
+    u, v, valid, Zp = O.reproject(D, K, T)
+    assert O.geometric_consistency(Zp, torch.full((B, 1, H, W), 2.0), u, v, valid).item() < 1e-7
+    got = O.geometric_consistency(Zp, torch.full((B, 1, H, W), 3.0), u, v, valid).item()
+    assert abs(got - valid.float().mean().item() * (1.0 / 5.0)) < 1e-6
