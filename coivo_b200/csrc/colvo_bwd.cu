@@ -35,7 +35,7 @@ __device__ __forceinline__ float smooth_grad(float s, float D, float inv, float 
 // the CTA stages the coefficient tile (+1 halo) in shared memory, then every thread warps its own
 // pixel once per source, gathers the 3x3 neighbourhood of coefficients, and pushes the result
 // through the LCC, bilinear and projection adjoints.
-template <int NS>
+template <int NS, bool GEO>
 __global__ void __launch_bounds__(kThreads, COLVO_MINB_BWD)
     k_photo_bwd(KP P, const float* __restrict__ grad_loss, const uint8_t* __restrict__ sel,
                 const double* __restrict__ saved_frame, const double* __restrict__ saved_scale,
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_BWD)
         // geometric consistency (f-2): gradient to Z' directly, to the sampled source depth (scatter) and,
         // through its spatial derivative, to (u', v')
         float dZp_direct = 0.f;
-        if (P.src_depth && g.valid) {
+        if (GEO && g.valid) {
           float d4[4], dZ, dS;
           const float ds = sample_plane(P.src_depth + (long long)(b * P.N + n) * P.HW, t, P.W, d4);
           geo_diff(g.Zp, ds, dZ, dS);
@@ -398,16 +398,19 @@ cudaError_t launch_backward(const KP& P, const BwdBuffers& Wk, const float* grad
   {
     ScopedKernelTimer tm(2, st);
     // opting in to > 48 KB of dynamic shared memory is a per-function, per-device attribute: cheap and idempotent
-    cudaFuncSetAttribute(k_photo_bwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)photo_bwd_smem<1>());
-    cudaFuncSetAttribute(k_photo_bwd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)photo_bwd_smem<2>());
-    if (P.N == 1)
-      k_photo_bwd<1><<<grid, kThreads, photo_bwd_smem<1>(), st>>>(P, grad_loss, sel, sv.frame, sv.scale, sv.s_field[0], sv.coef, grad_depth[0],
-                                                Wk.dDhat[1], Wk.dDhat[2], Wk.dDhat[3], grad_srcs, grad_src_depth,
-                                                                      Wk.pose_part);
-    else
-      k_photo_bwd<2><<<grid, kThreads, photo_bwd_smem<2>(), st>>>(P, grad_loss, sel, sv.frame, sv.scale, sv.s_field[0], sv.coef, grad_depth[0],
-                                                Wk.dDhat[1], Wk.dDhat[2], Wk.dDhat[3], grad_srcs, grad_src_depth,
-                                                                      Wk.pose_part);
+    auto launch = [&](auto kern, size_t smem) {
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      kern<<<grid, kThreads, smem, st>>>(P, grad_loss, sel, sv.frame, sv.scale, sv.s_field[0], sv.coef, grad_depth[0],
+                                         Wk.dDhat[1], Wk.dDhat[2], Wk.dDhat[3], grad_srcs, grad_src_depth, Wk.pose_part);
+    };
+    const bool geo = P.src_depth != nullptr;
+    if (P.N == 1) {
+      if (geo) launch(k_photo_bwd<1, true>, photo_bwd_smem<1>());
+      else launch(k_photo_bwd<1, false>, photo_bwd_smem<1>());
+    } else {
+      if (geo) launch(k_photo_bwd<2, true>, photo_bwd_smem<2>());
+      else launch(k_photo_bwd<2, false>, photo_bwd_smem<2>());
+    }
   }
   k_pose_final<<<P.B * P.N, kThreads, 0, st>>>(P, Wk.pose_part, grad_T);
   if (P.S > 1) {

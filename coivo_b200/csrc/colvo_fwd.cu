@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(kThreads)
 // ray, the up-sampled depth and the target pixel are loaded once.  The raw warped frames are also
 // written out ([B,N,S,3,H,W] scratch): the tile kernel needs them with a halo, and re-warping there
 // costs more issue slots than the 12 B/pixel round trip costs bandwidth on this ALU-bound path.
-template <int NS>
+template <int NS, bool GEO>
 __global__ void __launch_bounds__(kThreads, COLVO_MINB_STATS)
     k_warp_stats(KP P, double* __restrict__ part, uint8_t* __restrict__ valid_out, float* __restrict__ iw_out) {
   constexpr int NV = kStatVals * NS;
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_STATS)
           acc[kStatVals * n + 2] += (double)(y0 + y1 + y2);
           acc[kStatVals * n + 3] += (double)(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
           acc[kStatVals * n + 4] += (double)(x[0] * y0 + x[1] * y1 + x[2] * y2);
-          if (P.src_depth) {       // geometric consistency (f-2): per-pixel, so it lives in this pass
+          if (GEO) {               // geometric consistency (f-2): per-pixel, so it lives in this pass
             float d4[4], dZ, dS;
             const float ds = sample_plane(P.src_depth + (long long)(b * P.N + n) * P.HW, t, P.W, d4);
             acc[kStatVals * n + 5] += (double)geo_diff(g.Zp, ds, dZ, dS);
@@ -689,8 +689,14 @@ cudaError_t launch_forward(const KP& P, const FwdBuffers& Wk, float* loss, float
   {
     ScopedKernelTimer tm(3, st);
     dim3 g(Wk.stat_chunks, P.B * P.S);
-    if (P.N == 1) k_warp_stats<1><<<g, kThreads, 0, st>>>(P, Wk.stat_part, valid, Wk.iw);
-    else k_warp_stats<2><<<g, kThreads, 0, st>>>(P, Wk.stat_part, valid, Wk.iw);
+    const bool geo = P.src_depth != nullptr;
+    if (P.N == 1) {
+      if (geo) k_warp_stats<1, true><<<g, kThreads, 0, st>>>(P, Wk.stat_part, valid, Wk.iw);
+      else k_warp_stats<1, false><<<g, kThreads, 0, st>>>(P, Wk.stat_part, valid, Wk.iw);
+    } else {
+      if (geo) k_warp_stats<2, true><<<g, kThreads, 0, st>>>(P, Wk.stat_part, valid, Wk.iw);
+      else k_warp_stats<2, false><<<g, kThreads, 0, st>>>(P, Wk.stat_part, valid, Wk.iw);
+    }
   }
   k_lcc_solve<<<BNS, 32, 0, st>>>(P, Wk.stat_part, Wk.stat_chunks, ab, save ? sv.frame : nullptr);
   dim3 grid(P.tiles_x, P.tiles_y, P.B);
@@ -718,7 +724,7 @@ cudaError_t launch_forward(const KP& P, const FwdBuffers& Wk, float* loss, float
 
 cudaError_t launch_consistency(const KP& P, double* stat_part, int stat_chunks, double* pe_part, float* ab, float* out,
                                cudaStream_t st) {
-  k_warp_stats<1><<<dim3(stat_chunks, P.B), kThreads, 0, st>>>(P, stat_part, nullptr, nullptr);
+  k_warp_stats<1, false><<<dim3(stat_chunks, P.B), kThreads, 0, st>>>(P, stat_part, nullptr, nullptr);
   k_lcc_solve<<<P.B, 32, 0, st>>>(P, stat_part, stat_chunks, ab, nullptr);
   k_consistency_pe<<<dim3(P.tiles_x, P.tiles_y, P.B), kThreads, 0, st>>>(P, ab, pe_part);
   k_consistency_final<<<P.B, kThreads, 0, st>>>(P, pe_part, ab, out);
