@@ -23,6 +23,7 @@ F_LCC = 1
 F_LCC_DETACH = 2
 F_SAVE_FOR_BWD = 4
 F_NO_SRC_GRAD = 8
+F_PACKED_BF16 = 16
 
 MAX_SCALES = 4
 MAX_SOURCES = 2

@@ -57,9 +57,10 @@ void fill_params(KP& P, const ColvoDesc* d) {
   P.eps_disp = d->eps_disp; P.z_min = d->z_min; P.smooth_weight = d->smooth_weight;
   P.geo_weight = d->geo_weight;
   P.flags = d->flags;
-  P.tgt_bs = 3ll * P.HW;
-  P.src_ns = 3ll * P.HW;
-  P.src_bs = (long long)d->N * 3ll * P.HW;
+  P.tgt_bf = 1;
+  P.src_nf = 1;
+  P.src_bf = d->N;
+  P.frame_el = (d->flags & COLVO_F_PACKED_BF16) ? (long long)P.HW : 3ll * P.HW;
   P.K_bs = 9; P.T_ns = 16; P.T_bs = 16 * d->N;
   P.tiles_x = div_up(d->W, kTileW);
   P.tiles_y = div_up(d->H, kTileH);
@@ -135,7 +136,7 @@ const char* colvo_error_string(int rc) {
     case COLVO_E_WORKSPACE: return "colvo: workspace too small (see colvo_workspace_bytes)";
     case COLVO_E_NULL_PTR: return "colvo: required pointer is NULL";
     case COLVO_E_MISALIGNED: return "colvo: pointer not aligned (fp32 buffers 4 B, saved 8 B, workspace 256 B)";
-    case COLVO_E_UNSUPPORTED: return "colvo: unsupported configuration";
+    case COLVO_E_UNSUPPORTED: return "colvo: unsupported configuration (e.g. grad_srcs with packed bf16 images)";
     default: break;
   }
   if (rc > 0) return cudaGetErrorString(static_cast<cudaError_t>(rc));
@@ -173,7 +174,7 @@ int colvo_saved_doubles(const ColvoDesc* d, size_t* count) {
   return 0;
 }
 
-int colvo_photo_forward(const ColvoDesc* d, const float* tgt, const float* srcs, const float* const* depth,
+int colvo_photo_forward(const ColvoDesc* d, const void* tgt, const void* srcs, const float* const* depth,
                         const float* K, const float* T, const float* src_depth, float* loss, float* ab,
                         uint8_t* valid, uint8_t* sel, double* saved, void* ws, size_t ws_bytes, void* stream) {
   int rc = check_desc(d);
@@ -183,6 +184,7 @@ int colvo_photo_forward(const ColvoDesc* d, const float* tgt, const float* srcs,
     if (!depth[k]) return COLVO_E_NULL_PTR;
   if ((d->flags & COLVO_F_SAVE_FOR_BWD) && (!sel || !saved)) return COLVO_E_NULL_PTR;
   if (((uintptr_t)ws & 255u) || ((uintptr_t)saved & 15u)) return COLVO_E_MISALIGNED;
+  if ((d->flags & COLVO_F_PACKED_BF16) && ((((uintptr_t)tgt) | ((uintptr_t)srcs)) & 7u)) return COLVO_E_MISALIGNED;
   FwdBuffers F;
   if (carve_fwd(d, ws, F) > ws_bytes) return COLVO_E_WORKSPACE;
   KP P;
@@ -195,7 +197,7 @@ int colvo_photo_forward(const ColvoDesc* d, const float* tgt, const float* srcs,
   return (int)launch_forward(P, F, loss, ab, valid, sel, sv, static_cast<cudaStream_t>(stream));
 }
 
-int colvo_photo_backward(const ColvoDesc* d, const float* tgt, const float* srcs, const float* const* depth,
+int colvo_photo_backward(const ColvoDesc* d, const void* tgt, const void* srcs, const float* const* depth,
                          const float* K, const float* T, const float* src_depth, const float* grad_loss,
                          const uint8_t* sel, const double* saved, float* const* grad_depth, float* grad_T,
                          float* grad_srcs, float* grad_src_depth, void* ws, size_t ws_bytes, void* stream) {
@@ -207,7 +209,9 @@ int colvo_photo_backward(const ColvoDesc* d, const float* tgt, const float* srcs
     if (!depth[k] || !grad_depth[k]) return COLVO_E_NULL_PTR;
   const bool want_src = !(d->flags & COLVO_F_NO_SRC_GRAD);
   if (want_src && !grad_srcs) return COLVO_E_NULL_PTR;
+  if (want_src && (d->flags & COLVO_F_PACKED_BF16)) return COLVO_E_UNSUPPORTED;   // quantised images carry no gradient
   if (((uintptr_t)ws & 255u) || ((uintptr_t)saved & 15u)) return COLVO_E_MISALIGNED;
+  if ((d->flags & COLVO_F_PACKED_BF16) && ((((uintptr_t)tgt) | ((uintptr_t)srcs)) & 7u)) return COLVO_E_MISALIGNED;
   BwdBuffers Bw;
   if (carve_bwd(d, ws, Bw) > ws_bytes) return COLVO_E_WORKSPACE;
   KP P;
@@ -271,9 +275,9 @@ int colvo_consistency(int32_t F, int32_t H, int32_t W, uint32_t flags, const flo
   // pair i: target = frames[i], source = frames[i+1]: one array, two views
   P.tgt = frames;
   P.srcs = frames + 3ll * P.HW;
-  P.tgt_bs = 3ll * P.HW;
-  P.src_bs = 3ll * P.HW;
-  P.src_ns = 0;
+  P.tgt_bf = 1;
+  P.src_bf = 1;
+  P.src_nf = 0;
   P.depth[0] = depth;
   P.K = K;
   P.K_bs = k_per_pair ? 9 : 0;
@@ -359,6 +363,7 @@ int colvo_photo_step_host(const ColvoDesc* d_in, const float* h_tgt, const float
   const float* depth_p[kMaxS] = {A.depth[0], A.depth[1], A.depth[2], A.depth[3]};
   float* gdepth_p[kMaxS] = {A.grad_depth[0], A.grad_depth[1], A.grad_depth[2], A.grad_depth[3]};
   d.geo_weight = 0.f;   // the host step carries no source depth maps
+  d.flags &= ~COLVO_F_PACKED_BF16;   // ... and takes planar fp32 images
   rc = colvo_photo_forward(&d, A.tgt, A.srcs, depth_p, A.K, A.T, nullptr, A.loss, A.ab, nullptr, A.sel, A.saved, A.ws,
                            A.ws_bytes, stream);
   if (rc) return rc;

@@ -35,7 +35,7 @@ __device__ __forceinline__ float smooth_grad(float s, float D, float inv, float 
 // the CTA stages the coefficient tile (+1 halo) in shared memory, then every thread warps its own
 // pixel once per source, gathers the 3x3 neighbourhood of coefficients, and pushes the result
 // through the LCC, bilinear and projection adjoints.
-template <int NS, bool GEO>
+template <int NS, bool GEO, bool PK>
 __global__ void __launch_bounds__(kThreads, COLVO_MINB_BWD)
     k_photo_bwd(KP P, const float* __restrict__ grad_loss, const uint8_t* __restrict__ sel,
                 const double* __restrict__ saved_frame, const double* __restrict__ saved_scale,
@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_BWD)
   const bool in_img = (px < P.W) && (py < P.H);
   const int qx = imin(px, P.W - 1), qy = imin(py, P.H - 1);             // addressable stand-in when outside
   const int qo = qy * P.W + qx;
-  const float* tg = P.tgt + (long long)b * P.tgt_bs;
+  const Img<PK> tg = img_at<PK>(P, P.tgt, b * P.tgt_bf);
   const Cam cam = load_cam(P, b);
   const float go = __ldg(grad_loss);
   const float wscale = go / ((float)P.S * (float)P.B * (float)P.HW);
@@ -102,8 +102,7 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_BWD)
     mx3[d] = reflect_mult(px, px + d - 1, P.W);
   }
   float yq[3];
-#pragma unroll
-  for (int ch = 0; ch < 3; ++ch) yq[ch] = __ldg(tg + (ch * P.HW + qo));
+  tg.load3(qo, yq);
   const float own_rx = ray_x(qx, cam), own_ry = ray_y(qy, cam);
   const int oc = ty * kCW + tx;
 
@@ -172,12 +171,12 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_BWD)
 #pragma unroll
     for (int n = 0; n < NS; ++n) {
       if (in_img) {
-        const float* src = P.srcs + (long long)b * P.src_bs + (long long)n * P.src_ns;
+        const Img<PK> src = img_at<PK>(P, P.srcs, b * P.src_bf + n * P.src_nf);
         const Pose pose = load_pose(P, b, n);
         const float a = cst[n][k][0], bb = cst[n][k][1];
         const float Pc = cst[n][k][2], Qc = cst[n][k][3], mx = cst[n][k][4], my = cst[n][k][5];
         Geo g; Taps t; Texels tx4; float xq[3];
-        warp_sample(P, src, cam, pose, own_rx, own_ry, D_own, g, t, tx4, xq);
+        warp_sample<PK>(P, src, cam, pose, own_rx, own_ry, D_own, g, t, tx4, xq);
         const float wq = (sels[k][oc + kCW + 1] == (unsigned char)(NS + n)) ? wscale * (1.f - P.alpha) * (1.0f / 3.0f) : 0.f;
         float hq[3];
 #pragma unroll
@@ -189,7 +188,8 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_BWD)
         float du = 0.f, dv = 0.f;
         const float w00 = (1.f - t.wx) * (1.f - t.wy), w01 = t.wx * (1.f - t.wy);
         const float w10 = (1.f - t.wx) * t.wy, w11 = t.wx * t.wy;
-        float* gs = grad_srcs ? grad_srcs + (long long)b * P.src_bs + (long long)n * P.src_ns : nullptr;
+        // (grad_srcs is planar fp32 [B,N,3,H,W]; it is null for packed sources: quantised images carry no gradient)
+        float* gs = grad_srcs ? grad_srcs + (b * P.src_bf + n * P.src_nf) * (3ll * P.HW) : nullptr;
         float *g00 = gs + (t.y0 * P.W + t.x0), *g01 = gs + (t.y0 * P.W + t.x1);
         float *g10 = gs + (t.y1 * P.W + t.x0), *g11 = gs + (t.y1 * P.W + t.x1);
 #pragma unroll
@@ -403,13 +403,13 @@ cudaError_t launch_backward(const KP& P, const BwdBuffers& Wk, const float* grad
       kern<<<grid, kThreads, smem, st>>>(P, grad_loss, sel, sv.frame, sv.scale, sv.s_field[0], sv.coef, grad_depth[0],
                                          Wk.dDhat[1], Wk.dDhat[2], Wk.dDhat[3], grad_srcs, grad_src_depth, Wk.pose_part);
     };
-    const bool geo = P.src_depth != nullptr;
+    const bool geo = P.src_depth != nullptr, pk = (P.flags & 16u) != 0;
     if (P.N == 1) {
-      if (geo) launch(k_photo_bwd<1, true>, photo_bwd_smem<1>());
-      else launch(k_photo_bwd<1, false>, photo_bwd_smem<1>());
+      if (geo) { if (pk) launch(k_photo_bwd<1, true, true>, photo_bwd_smem<1>()); else launch(k_photo_bwd<1, true, false>, photo_bwd_smem<1>()); }
+      else { if (pk) launch(k_photo_bwd<1, false, true>, photo_bwd_smem<1>()); else launch(k_photo_bwd<1, false, false>, photo_bwd_smem<1>()); }
     } else {
-      if (geo) launch(k_photo_bwd<2, true>, photo_bwd_smem<2>());
-      else launch(k_photo_bwd<2, false>, photo_bwd_smem<2>());
+      if (geo) { if (pk) launch(k_photo_bwd<2, true, true>, photo_bwd_smem<2>()); else launch(k_photo_bwd<2, true, false>, photo_bwd_smem<2>()); }
+      else { if (pk) launch(k_photo_bwd<2, false, true>, photo_bwd_smem<2>()); else launch(k_photo_bwd<2, false, false>, photo_bwd_smem<2>()); }
     }
   }
   k_pose_final<<<P.B * P.N, kThreads, 0, st>>>(P, Wk.pose_part, grad_T);

@@ -52,6 +52,7 @@ static inline int total_chunks(const KP& P) {
 // blocks [0, n_pyr): target pyramid, one thread per output texel (block ranges per scale: pyr_off[k]);
 // blocks [n_pyr, ...): sum of 1/D chunks
 struct PyrOff { int off[kMaxS + 1]; };
+template <bool PK>
 __global__ void __launch_bounds__(kThreads)
     k_prepass(KP P, int n_pyr, PyrOff po, float* p1, float* p2, float* p3, double* __restrict__ disp_part) {
   __shared__ double sm[kThreads / 32];
@@ -66,11 +67,20 @@ __global__ void __launch_bounds__(kThreads)
     const int x = i % wk, r = i / wk;
     const int y = r % hk, bc = r / hk;
     const int b = bc / 3, c = bc - 3 * b;
-    const float* src = P.tgt + (long long)b * P.tgt_bs + (long long)c * P.HW + (y * f) * P.W + x * f;
+    const Img<PK> im = img_at<PK>(P, P.tgt, b * P.tgt_bf);
+    const int o = (y * f) * P.W + x * f;
     float s = 0.f;
     for (int dy = 0; dy < f; ++dy) {
       float rs = 0.f;
-      for (int dx = 0; dx < f; ++dx) rs += __ldg(src + dy * P.W + dx);
+      for (int dx = 0; dx < f; ++dx) {
+        if constexpr (PK) {
+          float v[3];
+          im.load3(o + dy * P.W + dx, v);
+          rs += (c == 0) ? v[0] : (c == 1 ? v[1] : v[2]);
+        } else {
+          rs += __ldg(im.p + (c * P.HW + o + dy * P.W + dx));
+        }
+      }
       s += rs;
     }
     out[i] = s * (1.0f / (float)(f * f));
@@ -91,15 +101,16 @@ __global__ void __launch_bounds__(kThreads)
 // ray, the up-sampled depth and the target pixel are loaded once.  The raw warped frames are also
 // written out ([B,N,S,3,H,W] scratch): the tile kernel needs them with a halo, and re-warping there
 // costs more issue slots than the 12 B/pixel round trip costs bandwidth on this ALU-bound path.
-template <int NS, bool GEO>
+template <int NS, bool GEO, bool PK>
 __global__ void __launch_bounds__(kThreads, COLVO_MINB_STATS)
     k_warp_stats(KP P, double* __restrict__ part, uint8_t* __restrict__ valid_out, float* __restrict__ iw_out) {
-  constexpr int NV = kStatVals * NS;
+  constexpr int NA = GEO ? kStatVals : 5;      // accumulators per source (the 6th only with the geometric term)
+  constexpr int NV = NA * NS;
   __shared__ double sm[(kThreads / 32) * NV];
   const int bk = blockIdx.y, k = bk % P.S, b = bk / P.S;
   const Cam cam = load_cam(P, b);
   const float* Dk = P.depth[k] + (long long)b * P.depth_bs[k];
-  const float* tg = P.tgt + (long long)b * P.tgt_bs;
+  const Img<PK> tg = img_at<PK>(P, P.tgt, b * P.tgt_bf);
   Pose pose[NS];
 #pragma unroll
   for (int n = 0; n < NS; ++n) pose[n] = load_pose(P, b, n);
@@ -113,12 +124,20 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_STATS)
     if (pix < P.HW) {
       const float rx = ray_x(px, cam), ry = ray_y(py, cam);
       const float D = depth_at(P, Dk, k, px, py);
-      const float y0 = __ldg(tg + pix), y1 = __ldg(tg + P.HW + pix), y2 = __ldg(tg + 2 * P.HW + pix);
+      float y0, y1, y2;
+      if constexpr (PK) {
+        float yv[3];
+        tg.load3(pix, yv);
+        y0 = yv[0]; y1 = yv[1]; y2 = yv[2];
+      } else {
+        y0 = __ldg(tg.p + pix); y1 = __ldg(tg.p + P.HW + pix); y2 = __ldg(tg.p + 2 * P.HW + pix);
+      }
 #pragma unroll
       for (int n = 0; n < NS; ++n) {
-        const float* src = P.srcs + (long long)b * P.src_bs + (long long)n * P.src_ns;
+        // (built per use on purpose: a hoisted 64-bit base costs this 64-register kernel more than re-deriving it)
+        const Img<PK> src = img_at<PK>(P, P.srcs, b * P.src_bf + n * P.src_nf);
         Geo g; Taps t; Texels tx; float x[3];
-        warp_sample(P, src, cam, pose[n], rx, ry, D, g, t, tx, x);
+        warp_sample<PK>(P, src, cam, pose[n], rx, ry, D, g, t, tx, x);
         const int bnk = (b * P.N + n) * P.S + k;
         if (valid_out) valid_out[(long long)bnk * P.HW + pix] = g.valid ? 1 : 0;
         if (iw_out) {          // raw warped frame, re-used by k_photo_fwd instead of warping again (+halo)
@@ -128,15 +147,15 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_STATS)
           o[2 * (long long)P.HW] = x[2];
         }
         if (g.valid) {
-          acc[kStatVals * n + 0] += 3.0;
-          acc[kStatVals * n + 1] += (double)(x[0] + x[1] + x[2]);
-          acc[kStatVals * n + 2] += (double)(y0 + y1 + y2);
-          acc[kStatVals * n + 3] += (double)(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
-          acc[kStatVals * n + 4] += (double)(x[0] * y0 + x[1] * y1 + x[2] * y2);
+          acc[NA * n + 0] += 3.0;
+          acc[NA * n + 1] += (double)(x[0] + x[1] + x[2]);
+          acc[NA * n + 2] += (double)(y0 + y1 + y2);
+          acc[NA * n + 3] += (double)(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+          acc[NA * n + 4] += (double)(x[0] * y0 + x[1] * y1 + x[2] * y2);
           if (GEO) {               // geometric consistency (f-2): per-pixel, so it lives in this pass
             float d4[4], dZ, dS;
             const float ds = sample_plane(P.src_depth + (long long)(b * P.N + n) * P.HW, t, P.W, d4);
-            acc[kStatVals * n + 5] += (double)geo_diff(g.Zp, ds, dZ, dS);
+            acc[NA * n + (NA - 1)] += (double)geo_diff(g.Zp, ds, dZ, dS);
           }
         }
       }
@@ -156,7 +175,7 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_STATS)
     double s = 0.0;
 #pragma unroll
     for (int w = 0; w < kThreads / 32; ++w) s += sm[w * NV + threadIdx.x];
-    const int n = threadIdx.x / kStatVals, j = threadIdx.x - kStatVals * n;
+    const int n = threadIdx.x / NA, j = threadIdx.x - NA * n;
     const int bnk = (b * P.N + n) * P.S + k;
     part[((long long)bnk * gridDim.x + blockIdx.x) * kStatVals + j] = s;
   }
@@ -268,7 +287,7 @@ __device__ __forceinline__ void ywin_init(YWin& y, const float* ys, int own) {
   }
 }
 
-template <int NS>
+template <int NS, bool PK>
 __global__ void __launch_bounds__(kThreads, COLVO_MINB_FWD)
     k_photo_fwd(KP P, const float* __restrict__ ab, uint8_t* __restrict__ sel_out, double* __restrict__ loss_part,
                 double* __restrict__ g_part, int need_g, float* __restrict__ coef_out, const float* __restrict__ iw) {
@@ -285,7 +304,7 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_FWD)
   const int px = x0 + tx, py = y0 + ty;
   const bool in_img = (px < P.W) && (py < P.H);
   const int own = ty * kFW + tx;
-  const float* tg = P.tgt + (long long)b * P.tgt_bs;
+  const Img<PK> tg = img_at<PK>(P, P.tgt, b * P.tgt_bf);
 
   // the (at most) two halo-tile positions this thread fills for every frame (reflect-padded coordinates)
   int pso[2], pgo[2];
@@ -301,14 +320,27 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_FWD)
   // Frame sequence of this tile: f < NS the raw sources (identity candidates), then f = NS + k*NS + n the
   // warped frames.  Frame f+1 is fetched with cp.async into the other buffer while frame f is evaluated.
   auto stage = [&](int f) {
+    float* xb = xs[f & 1];
+    if (PK && f < NS) {   // packed bf16 sources are widened on the way in: plain loads (2 of the 2 + 2S frames)
+      const Img<PK> im = img_at<PK>(P, P.srcs, b * P.src_bf + f * P.src_nf);
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+        if (pok[j]) {
+          float v[3];
+          im.load3(pgo[j], v);
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) xb[ch * kFN + pso[j]] = v[ch];
+        }
+      cp_async_commit();   // (empty group: keeps the wait/commit pairing uniform)
+      return;
+    }
     const float* p;
     if (f < NS) {
-      p = P.srcs + (long long)b * P.src_bs + (long long)f * P.src_ns;
+      p = static_cast<const float*>(P.srcs) + (b * P.src_bf + f * P.src_nf) * P.frame_el;
     } else {
       const int k = (f - NS) / NS, n = (f - NS) % NS;
       p = iw + (long long)((b * P.N + n) * P.S + k) * 3 * P.HW;
     }
-    float* xb = xs[f & 1];
 #pragma unroll
     for (int j = 0; j < 2; ++j)
       if (pok[j]) {
@@ -322,8 +354,10 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_FWD)
 #pragma unroll
   for (int j = 0; j < 2; ++j)
     if (pok[j]) {
+      float v[3];
+      tg.load3(pgo[j], v);
 #pragma unroll
-      for (int ch = 0; ch < 3; ++ch) ys[ch * kFN + pso[j]] = __ldg(tg + (ch * P.HW + pgo[j]));
+      for (int ch = 0; ch < 3; ++ch) ys[ch * kFN + pso[j]] = v[ch];
     }
   __syncthreads();
 
@@ -448,7 +482,7 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_FWD)
 // ------------------------------------------------------------------------------------------
 // Smoothness (row 9).  Each pixel visits its four edges: the right/down ones give the loss, all
 // four give s_p = dL/dd*_p (for grad_loss = 1), which the backward only has to rescale.
-template <bool SAVE>
+template <bool SAVE, bool PK>
 __global__ void __launch_bounds__(kThreads)
     k_smooth_fwd(KP P, const double* __restrict__ disp_part, const float* p1, const float* p2, const float* p3,
                  double* __restrict__ smooth_part, double* __restrict__ saved_scale, float* s0, float* s1, float* s2,
@@ -471,45 +505,53 @@ __global__ void __launch_bounds__(kThreads)
   __syncthreads();
   const float inv = (float)(1.0 / (mean_s + (double)P.eps_disp));
   const float* D = P.depth[k] + (long long)b * P.depth_bs[k];
-  const float* I;
-  int cs;
-  if (k == 0) { I = P.tgt + (long long)b * P.tgt_bs; cs = P.HW; }
-  else { I = ((k == 1) ? p1 : (k == 2 ? p2 : p3)) + (long long)b * 3 * n; cs = n; }
+  // image of this scale: the target itself (either storage format) at k = 0, the fp32 pyramid above
+  const Img<PK> I0 = img_at<PK>(P, P.tgt, b * P.tgt_bf);
+  Img<false> Ik;
+  Ik.p = (k == 0) ? nullptr : ((k == 1) ? p1 : (k == 2 ? p2 : p3)) + (long long)b * 3 * n;
+  Ik.HW = n;
   float* sf = nullptr;
   if (SAVE) sf = ((k == 0) ? s0 : (k == 1 ? s1 : (k == 2 ? s2 : s3))) + (long long)b * n;
   const double lam = (double)P.smooth_weight / (double)(1 << k) / (double)P.S;
   const double nx = (double)P.B * hk * (wk - 1), ny = (double)P.B * (hk - 1) * wk;
   const float cx = nx > 0 ? (float)(lam / nx) : 0.f, cy = ny > 0 ? (float)(lam / ny) : 0.f;
   double acc[3] = {0.0, 0.0, 0.0};
-  for (int i = c * kThreads + threadIdx.x; i < n; i += C * kThreads) {
-    const int y = i / wk, x = i - y * wk;
-    const float dr = f_rcp(__ldg(D + i));
-    const float d = dr * inv;
-    const float i0 = __ldg(I + i), i1 = __ldg(I + cs + i), i2 = __ldg(I + 2 * cs + i);
-    float s = 0.f;
-    auto edge = [&](int j) -> float2 {   // (d_i - d_j, exp(-mean_c |I_i - I_j|))
-      float dn = f_rcp(__ldg(D + j)) * inv;
-      float e = (fabsf(i0 - __ldg(I + j)) + fabsf(i1 - __ldg(I + cs + j)) + fabsf(i2 - __ldg(I + 2 * cs + j))) *
-                (1.0f / 3.0f);
-      return make_float2(d - dn, __expf(-e));   // e in [0, 1]: MUFU.EX2 path, rel. error ~1e-6
-    };
-    if (x + 1 < wk) {
-      float2 t = edge(i + 1);
-      acc[0] += (double)(fabsf(t.x) * t.y);
-      if (SAVE) s += sgn(t.x) * t.y * cx;
+  auto run = [&](const auto& img) {
+    for (int i = c * kThreads + threadIdx.x; i < n; i += C * kThreads) {
+      const int y = i / wk, x = i - y * wk;
+      const float dr = f_rcp(__ldg(D + i));
+      const float d = dr * inv;
+      float iv[3];
+      img.load3(i, iv);
+      const float i0 = iv[0], i1 = iv[1], i2 = iv[2];
+      float s = 0.f;
+      auto edge = [&](int j) -> float2 {   // (d_i - d_j, exp(-mean_c |I_i - I_j|))
+        float dn = f_rcp(__ldg(D + j)) * inv;
+        float jv[3];
+        img.load3(j, jv);
+        float e = (fabsf(i0 - jv[0]) + fabsf(i1 - jv[1]) + fabsf(i2 - jv[2])) * (1.0f / 3.0f);
+        return make_float2(d - dn, __expf(-e));   // e in [0, 1]: MUFU.EX2 path, rel. error ~1e-6
+      };
+      if (x + 1 < wk) {
+        float2 t = edge(i + 1);
+        acc[0] += (double)(fabsf(t.x) * t.y);
+        if (SAVE) s += sgn(t.x) * t.y * cx;
+      }
+      if (y + 1 < hk) {
+        float2 t = edge(i + wk);
+        acc[1] += (double)(fabsf(t.x) * t.y);
+        if (SAVE) s += sgn(t.x) * t.y * cy;
+      }
+      if (SAVE) {
+        if (x > 0) { float2 t = edge(i - 1); s += sgn(t.x) * t.y * cx; }
+        if (y > 0) { float2 t = edge(i - wk); s += sgn(t.x) * t.y * cy; }
+        sf[i] = s;
+        acc[2] += (double)(s * dr);
+      }
     }
-    if (y + 1 < hk) {
-      float2 t = edge(i + wk);
-      acc[1] += (double)(fabsf(t.x) * t.y);
-      if (SAVE) s += sgn(t.x) * t.y * cy;
-    }
-    if (SAVE) {
-      if (x > 0) { float2 t = edge(i - 1); s += sgn(t.x) * t.y * cx; }
-      if (y > 0) { float2 t = edge(i - wk); s += sgn(t.x) * t.y * cy; }
-      sf[i] = s;
-      acc[2] += (double)(s * dr);
-    }
-  }
+  };
+  if (k == 0) run(I0);
+  else run(Ik);
   block_reduce_store<3, double>(acc, sm, smooth_part + ((long long)bk * kSmoothMaxChunks + c) * 3);
 }
 
@@ -611,8 +653,8 @@ __global__ void __launch_bounds__(kThreads, 2)
   const int px = x0 + tx, py = y0 + ty;
   const bool in_img = (px < P.W) && (py < P.H);
   const int own = ty * kFW + tx;
-  const float* tg = P.tgt + (long long)b * P.tgt_bs;
-  const float* src = P.srcs + (long long)b * P.src_bs;
+  const float* tg = static_cast<const float*>(P.tgt) + b * P.tgt_bf * P.frame_el;
+  const Img<false> src = img_at<false>(P, P.srcs, b * P.src_bf);
   const float* Dk = P.depth[0] + (long long)b * P.depth_bs[0];
   const Cam cam = load_cam(P, b);
   const Pose pose = load_pose(P, b, 0);
@@ -624,7 +666,7 @@ __global__ void __launch_bounds__(kThreads, 2)
     for (int ch = 0; ch < 3; ++ch) ys[ch * kFN + idx] = __ldg(tg + (ch * P.HW + gy * P.W + gx));
     if (ry <= P.H && rx <= P.W) {
       Geo g; Taps t; Texels tx4; float x[3];
-      warp_sample(P, src, cam, pose, ray_x(gx, cam), ray_y(gy, cam), __ldg(Dk + gy * P.W + gx), g, t, tx4, x);
+      warp_sample<false>(P, src, cam, pose, ray_x(gx, cam), ray_y(gy, cam), __ldg(Dk + gy * P.W + gx), g, t, tx4, x);
       xs[idx] = x[0];
       xs[kFN + idx] = x[1];
       xs[2 * kFN + idx] = x[2];
@@ -685,37 +727,40 @@ cudaError_t launch_forward(const KP& P, const FwdBuffers& Wk, float* loss, float
     else po.off[kMaxS] = n_pyr;
     if (k < P.S) n_pyr += div_up(P.B * 3 * P.h[k] * P.w[k], kThreads);
   }
-  k_prepass<<<n_pyr + chunks, kThreads, 0, st>>>(P, n_pyr, po, Wk.pyr[1], Wk.pyr[2], Wk.pyr[3], Wk.disp_part);
+  const bool pk = (P.flags & 16u) != 0;
+  if (pk) k_prepass<true><<<n_pyr + chunks, kThreads, 0, st>>>(P, n_pyr, po, Wk.pyr[1], Wk.pyr[2], Wk.pyr[3], Wk.disp_part);
+  else k_prepass<false><<<n_pyr + chunks, kThreads, 0, st>>>(P, n_pyr, po, Wk.pyr[1], Wk.pyr[2], Wk.pyr[3], Wk.disp_part);
   {
     ScopedKernelTimer tm(3, st);
     dim3 g(Wk.stat_chunks, P.B * P.S);
     const bool geo = P.src_depth != nullptr;
+    auto run = [&](auto kern) { kern<<<g, kThreads, 0, st>>>(P, Wk.stat_part, valid, Wk.iw); };
     if (P.N == 1) {
-      if (geo) k_warp_stats<1, true><<<g, kThreads, 0, st>>>(P, Wk.stat_part, valid, Wk.iw);
-      else k_warp_stats<1, false><<<g, kThreads, 0, st>>>(P, Wk.stat_part, valid, Wk.iw);
+      if (geo) { if (pk) run(k_warp_stats<1, true, true>); else run(k_warp_stats<1, true, false>); }
+      else { if (pk) run(k_warp_stats<1, false, true>); else run(k_warp_stats<1, false, false>); }
     } else {
-      if (geo) k_warp_stats<2, true><<<g, kThreads, 0, st>>>(P, Wk.stat_part, valid, Wk.iw);
-      else k_warp_stats<2, false><<<g, kThreads, 0, st>>>(P, Wk.stat_part, valid, Wk.iw);
+      if (geo) { if (pk) run(k_warp_stats<2, true, true>); else run(k_warp_stats<2, true, false>); }
+      else { if (pk) run(k_warp_stats<2, false, true>); else run(k_warp_stats<2, false, false>); }
     }
   }
   k_lcc_solve<<<BNS, 32, 0, st>>>(P, Wk.stat_part, Wk.stat_chunks, ab, save ? sv.frame : nullptr);
   dim3 grid(P.tiles_x, P.tiles_y, P.B);
   {
     ScopedKernelTimer tm(1, st);
-    if (P.N == 1)
-      k_photo_fwd<1><<<grid, kThreads, 0, st>>>(P, ab, sel, Wk.loss_part, Wk.g_part, need_g, save ? sv.coef : nullptr,
-                                                Wk.iw);
-    else
-      k_photo_fwd<2><<<grid, kThreads, 0, st>>>(P, ab, sel, Wk.loss_part, Wk.g_part, need_g, save ? sv.coef : nullptr,
-                                                Wk.iw);
+    float* co = save ? sv.coef : nullptr;
+    auto run = [&](auto kern) { kern<<<grid, kThreads, 0, st>>>(P, ab, sel, Wk.loss_part, Wk.g_part, need_g, co, Wk.iw); };
+    if (P.N == 1) { if (pk) run(k_photo_fwd<1, true>); else run(k_photo_fwd<1, false>); }
+    else { if (pk) run(k_photo_fwd<2, true>); else run(k_photo_fwd<2, false>); }
   }
-  if (save)
-    k_smooth_fwd<true><<<chunks, kThreads, 0, st>>>(P, Wk.disp_part, Wk.pyr[1], Wk.pyr[2], Wk.pyr[3], Wk.smooth_part,
-                                                    sv.scale, sv.s_field[0], sv.s_field[1], sv.s_field[2],
-                                                    sv.s_field[3]);
-  else
-    k_smooth_fwd<false><<<chunks, kThreads, 0, st>>>(P, Wk.disp_part, Wk.pyr[1], Wk.pyr[2], Wk.pyr[3], Wk.smooth_part,
-                                                     nullptr, nullptr, nullptr, nullptr, nullptr);
+  {
+    auto run = [&](auto kern, bool sv_on) {
+      kern<<<chunks, kThreads, 0, st>>>(P, Wk.disp_part, Wk.pyr[1], Wk.pyr[2], Wk.pyr[3], Wk.smooth_part, sv_on ? sv.scale : nullptr,
+                                        sv_on ? sv.s_field[0] : nullptr, sv_on ? sv.s_field[1] : nullptr,
+                                        sv_on ? sv.s_field[2] : nullptr, sv_on ? sv.s_field[3] : nullptr);
+    };
+    if (save) { if (pk) run(k_smooth_fwd<true, true>, true); else run(k_smooth_fwd<true, false>, true); }
+    else { if (pk) run(k_smooth_fwd<false, true>, false); else run(k_smooth_fwd<false, false>, false); }
+  }
   const int nfin = 1 + (save ? BNS + P.B * P.S : 0);
   k_finalize_fwd<<<nfin, kThreads, 0, st>>>(P, Wk.loss_part, Wk.g_part, Wk.smooth_part, Wk.stat_part, Wk.stat_chunks,
                                             loss, sv.frame, sv.scale, need_g);
@@ -724,7 +769,7 @@ cudaError_t launch_forward(const KP& P, const FwdBuffers& Wk, float* loss, float
 
 cudaError_t launch_consistency(const KP& P, double* stat_part, int stat_chunks, double* pe_part, float* ab, float* out,
                                cudaStream_t st) {
-  k_warp_stats<1, false><<<dim3(stat_chunks, P.B), kThreads, 0, st>>>(P, stat_part, nullptr, nullptr);
+  k_warp_stats<1, false, false><<<dim3(stat_chunks, P.B), kThreads, 0, st>>>(P, stat_part, nullptr, nullptr);
   k_lcc_solve<<<P.B, 32, 0, st>>>(P, stat_part, stat_chunks, ab, nullptr);
   k_consistency_pe<<<dim3(P.tiles_x, P.tiles_y, P.B), kThreads, 0, st>>>(P, ab, pe_part);
   k_consistency_final<<<P.B, kThreads, 0, st>>>(P, pe_part, ab, out);

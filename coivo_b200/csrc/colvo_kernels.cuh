@@ -33,14 +33,16 @@ struct KP {
   int sm_chunks[kMaxS];              // smoothness CTAs per (b, k)
   float alpha, c1, c2, eps_proj, eps_lcc, eps_disp, z_min, smooth_weight;
   unsigned flags;
-  const float* tgt;                  // [B,3,H,W]
-  const float* srcs;                 // [B,N,3,H,W]
+  const void* tgt;                   // [B,3,H,W] fp32 planar, or [B,H,W,4] bf16 packed (COLVO_F_PACKED_BF16)
+  const void* srcs;                  // [B,N,3,H,W] fp32 planar, or [B,N,H,W,4] bf16 packed
   const float* depth[kMaxS];         // [B,1,h_k,w_k]
   const float* K;                    // [B,3,3]
   const float* T;                    // [B,N,4,4]
   const float* src_depth;            // [B,N,1,H,W] or null: geometric-consistency term (f-2)
   float geo_weight;
-  long long tgt_bs, src_bs, src_ns;  // element strides (the consistency sweep aliases one frame array)
+  int tgt_bf, src_bf, src_nf;        // strides in FRAMES (one frame = one [3,H,W] image): target b -> b*tgt_bf,
+                                     // source (b,n) -> b*src_bf + n*src_nf (the consistency sweep aliases one array)
+  long long frame_el;                // elements per frame in the storage format: 3*HW floats, or HW 8-byte texels
   long long depth_bs[kMaxS];
   int K_bs, T_bs, T_ns;
   int tiles_x, tiles_y;
@@ -81,28 +83,94 @@ __device__ __forceinline__ float depth_at(const KP& P, const float* __restrict__
   return upsample_blend(d00, d01, d10, d11, ax.w1, ay.w1);
 }
 
+// One [3,H,W] frame in either storage format.  Planar fp32: three planes HW apart.  Packed: one 8-byte
+// RGBA-bf16 texel per pixel: a single load yields the three channels, widened
+// to fp32 by a shift / mask -- all arithmetic stays fp32.
+struct Texels { float i00[3], i01[3], i10[3], i11[3]; };
+template <bool PK> struct Img;
+template <> struct Img<false> {
+  const float* p;
+  int HW;
+  // the four bilinear taps of all three planes: four tap pointers, then + HW per plane (one IMAD.WIDE per load)
+  __device__ __forceinline__ void load_taps(int o00, int o01, int o10, int o11, Texels& tx) const {
+    const float *p00 = p + o00, *p01 = p + o01, *p10 = p + o10, *p11 = p + o11;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      tx.i00[c] = __ldg(p00);
+      tx.i01[c] = __ldg(p01);
+      tx.i10[c] = __ldg(p10);
+      tx.i11[c] = __ldg(p11);
+      p00 += HW; p01 += HW; p10 += HW; p11 += HW;
+    }
+  }
+  __device__ __forceinline__ void load3(int off, float (&v)[3]) const {
+    const float* q = p + off;     // one IMAD.WIDE, then + HW per plane
+    v[0] = __ldg(q);
+    q += HW;
+    v[1] = __ldg(q);
+    q += HW;
+    v[2] = __ldg(q);
+  }
+};
+template <> struct Img<true> {
+  const uint2* p;
+  int HW;
+  __device__ __forceinline__ void load_taps(int o00, int o01, int o10, int o11, Texels& tx) const {
+    load3(o00, tx.i00);
+    load3(o01, tx.i01);
+    load3(o10, tx.i10);
+    load3(o11, tx.i11);
+  }
+  __device__ __forceinline__ void load3(int off, float (&v)[3]) const {
+    const uint2 q = __ldg(p + off);
+    v[0] = __uint_as_float(q.x << 16);
+    v[1] = __uint_as_float(q.x & 0xffff0000u);
+    v[2] = __uint_as_float(q.y << 16);
+  }
+};
+// frame index (small) times the per-frame element count P.frame_el
+template <bool PK>
+__device__ __forceinline__ Img<PK> img_at(const KP& P, const void* base, int frame);
+template <>
+__device__ __forceinline__ Img<false> img_at<false>(const KP& P, const void* base, int frame) {
+  Img<false> im;
+  im.p = static_cast<const float*>(base) + frame * P.frame_el;
+  im.HW = P.HW;
+  return im;
+}
+template <>
+__device__ __forceinline__ Img<true> img_at<true>(const KP& P, const void* base, int frame) {
+  Img<true> im;
+  im.p = static_cast<const uint2*>(base) + frame * P.frame_el;
+  im.HW = P.HW;
+  return im;
+}
+
 // Rows 1-4 for one pixel whose ray (rx, ry) and up-sampled depth D are already known (both are
 // shared by the N sources; the ray also by the S scales): geometry, taps, 12 texels, 3 channels.
 // `src` is the [3][H][W] plane set of one source frame; offsets stay 32-bit (3*HW < 2^31).
-struct Texels { float i00[3], i01[3], i10[3], i11[3]; };
-__device__ __forceinline__ void warp_sample(const KP& P, const float* __restrict__ src, const Cam& cam,
-                                            const Pose& pose, float rx, float ry, float D, Geo& g, Taps& t,
-                                            Texels& tx, float (&x)[3]) {
+template <bool PK>
+__device__ __forceinline__ void warp_sample(const KP& P, const Img<PK>& src, const Cam& cam, const Pose& pose, float rx,
+                                            float ry, float D, Geo& g, Taps& t, Texels& tx, float (&x)[3]) {
   g = reproject_ray(rx, ry, D, cam, pose, P.W, P.H, P.eps_proj, P.z_min);
   t = make_taps(g.u, g.v, P.W, P.H);
   const int r0 = t.y0 * P.W, r1 = t.y1 * P.W;
-  // one IMAD.WIDE per address: four tap pointers, then + HW per channel plane
-  const float* p00 = src + (r0 + t.x0);
-  const float* p01 = src + (r0 + t.x1);
-  const float* p10 = src + (r1 + t.x0);
-  const float* p11 = src + (r1 + t.x1);
+  if constexpr (PK) {
+    src.load_taps(r0 + t.x0, r0 + t.x1, r1 + t.x0, r1 + t.x1, tx);
+  } else {
+    // one IMAD.WIDE per address: four tap pointers, then + HW (a constant-bank operand) per channel plane
+    const float* p00 = src.p + (r0 + t.x0);
+    const float* p01 = src.p + (r0 + t.x1);
+    const float* p10 = src.p + (r1 + t.x0);
+    const float* p11 = src.p + (r1 + t.x1);
 #pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    tx.i00[c] = __ldg(p00);
-    tx.i01[c] = __ldg(p01);
-    tx.i10[c] = __ldg(p10);
-    tx.i11[c] = __ldg(p11);
-    p00 += P.HW; p01 += P.HW; p10 += P.HW; p11 += P.HW;
+    for (int c = 0; c < 3; ++c) {
+      tx.i00[c] = __ldg(p00);
+      tx.i01[c] = __ldg(p01);
+      tx.i10[c] = __ldg(p10);
+      tx.i11[c] = __ldg(p11);
+      p00 += P.HW; p01 += P.HW; p10 += P.HW; p11 += P.HW;
+    }
   }
 #pragma unroll
   for (int c = 0; c < 3; ++c) x[c] = bilerp(tx.i00[c], tx.i01[c], tx.i10[c], tx.i11[c], t.wx, t.wy);

@@ -20,18 +20,47 @@ import torch
 from . import _lib
 
 
+def pack_images(x: torch.Tensor) -> torch.Tensor:
+    """`[...,3,H,W]` float -> `[...,H,W,4]` bfloat16, RGBA-interleaved (A = 0): the packed image storage of
+    SURVEY.md section 8(f)-3.  8 bytes per pixel instead of 12; one load per bilinear tap instead of three.
+    The loss computes in fp32 on the widened values, so parity holds against the oracle run on
+    `unpack_images(pack_images(x))`."""
+    if x.shape[-3] != 3:
+        raise ValueError("expected [...,3,H,W]")
+    pad = torch.zeros_like(x[..., :1, :, :])
+    return torch.cat([x, pad], dim=-3).movedim(-3, -1).contiguous().to(torch.bfloat16)
+
+
+def unpack_images(p: torch.Tensor) -> torch.Tensor:
+    """Inverse of `pack_images` (exact): `[...,H,W,4]` bfloat16 -> `[...,3,H,W]` float32."""
+    if p.shape[-1] != 4 or p.dtype != torch.bfloat16:
+        raise ValueError("expected [...,H,W,4] bfloat16")
+    return p[..., :3].to(torch.float32).movedim(-1, -3).contiguous()
+
+
 def _check_inputs(depth, pose, K, tgt, srcs):
+    """Returns (B, N, S, H, W, packed)."""
     if not isinstance(depth, (list, tuple)) or not 1 <= len(depth) <= _lib.MAX_SCALES:
         raise ValueError(f"depth must be a sequence of 1..{_lib.MAX_SCALES} tensors [B,1,h_k,w_k]")
     tensors = list(depth) + [pose, K, tgt, srcs]
     for t in tensors:
         if not isinstance(t, torch.Tensor):
             raise TypeError("all inputs must be torch.Tensor")
-    if tgt.dim() != 4 or tgt.shape[1] != 3:
-        raise ValueError("tgt must be [B,3,H,W]")
-    B, _, H, W = tgt.shape
-    if srcs.dim() != 5 or srcs.shape[0] != B or tuple(srcs.shape[2:]) != (3, H, W):
-        raise ValueError("srcs must be [B,N,3,H,W]")
+    packed = tgt.dtype == torch.bfloat16
+    if packed:
+        if tgt.dim() != 4 or tgt.shape[-1] != 4:
+            raise ValueError("packed tgt must be [B,H,W,4] bfloat16 (see pack_images)")
+        B, H, W, _ = tgt.shape
+        if srcs.dtype != torch.bfloat16 or srcs.dim() != 5 or srcs.shape[0] != B or tuple(srcs.shape[2:]) != (H, W, 4):
+            raise ValueError("packed srcs must be [B,N,H,W,4] bfloat16")
+        if srcs.requires_grad or tgt.requires_grad:
+            raise ValueError("packed bf16 images are data: they cannot require grad")
+    else:
+        if tgt.dim() != 4 or tgt.shape[1] != 3:
+            raise ValueError("tgt must be [B,3,H,W]")
+        B, _, H, W = tgt.shape
+        if srcs.dim() != 5 or srcs.shape[0] != B or tuple(srcs.shape[2:]) != (3, H, W):
+            raise ValueError("srcs must be [B,N,3,H,W]")
     N = srcs.shape[1]
     if not 1 <= N <= _lib.MAX_SOURCES:
         raise ValueError(f"1 <= N <= {_lib.MAX_SOURCES} source frames are supported")
@@ -43,9 +72,9 @@ def _check_inputs(depth, pose, K, tgt, srcs):
     for k, d in enumerate(depth):
         if tuple(d.shape) != (B, 1, H >> k, W >> k):
             raise ValueError(f"depth[{k}] must be [B,1,{H >> k},{W >> k}], got {tuple(d.shape)}")
-    for t in tensors:
+    for t in list(depth) + [pose, K] + ([] if packed else [tgt, srcs]):
         if t.dtype != torch.float32:
-            raise TypeError("all inputs must be float32")
+            raise TypeError("all inputs must be float32 (images may also be packed bfloat16, see pack_images)")
     dev = tgt.device
     for t in tensors:
         if t.device.type != "cuda":
@@ -54,7 +83,7 @@ def _check_inputs(depth, pose, K, tgt, srcs):
             raise ValueError("all inputs must live on the same device")
         if not t.is_contiguous():
             raise ValueError("inputs must be contiguous (NCHW); call .contiguous() outside the timed path")
-    return B, N, S, H, W
+    return B, N, S, H, W, packed
 
 
 class _Workspace:
@@ -75,7 +104,7 @@ class _Workspace:
 class _PhotoLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pose, K, tgt, srcs, alpha, smooth_weight, lcc, lcc_detach, want_valid, src_depth, geo_weight, *depth):
-        B, N, S, H, W = _check_inputs(depth, pose, K, tgt, srcs)
+        B, N, S, H, W, packed = _check_inputs(depth, pose, K, tgt, srcs)
         if src_depth is not None:
             if tuple(src_depth.shape) != (B, N, 1, H, W):
                 raise ValueError("src_depth must be [B,N,1,H,W]")
@@ -88,7 +117,7 @@ class _PhotoLossFn(torch.autograd.Function):
         lib = _lib.load()
         dev = tgt.device
         needs_grad = any(ctx.needs_input_grad[i] for i in (0, 3, 9)) or any(ctx.needs_input_grad[11:])
-        flags = (_lib.F_LCC if lcc else 0) | (_lib.F_LCC_DETACH if lcc_detach else 0)
+        flags = (_lib.F_LCC if lcc else 0) | (_lib.F_LCC_DETACH if lcc_detach else 0) | (_lib.F_PACKED_BF16 if packed else 0)
         if needs_grad:
             flags |= _lib.F_SAVE_FOR_BWD
         desc = _lib.make_desc(B, N, S, H, W, flags, alpha, smooth_weight, geo_weight)
@@ -128,7 +157,7 @@ class _PhotoLossFn(torch.autograd.Function):
         src_depth = ctx.saved_tensors[6] if ctx.has_src_depth else None
         depth = ctx.saved_tensors[7:] if ctx.has_src_depth else ctx.saved_tensors[6:]
         B, N, S, H, W, flags, alpha, smooth_weight, geo_weight = ctx.desc_args
-        want_src = ctx.needs_input_grad[3]
+        want_src = ctx.needs_input_grad[3] and not (flags & _lib.F_PACKED_BF16)
         if not want_src:
             flags |= _lib.F_NO_SRC_GRAD
         lib = _lib.load()

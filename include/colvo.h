@@ -39,6 +39,9 @@ extern "C" {
 #define COLVO_F_LCC_DETACH 2u      /* do not differentiate through (a, b)                       */
 #define COLVO_F_SAVE_FOR_BWD 4u    /* forward also produces what colvo_photo_backward needs     */
 #define COLVO_F_NO_SRC_GRAD 8u     /* backward: skip the scatter-add into grad_srcs             */
+#define COLVO_F_PACKED_BF16 16u    /* tgt / srcs are RGBA-interleaved bf16 ([..,H,W,4], 8 B per pixel, A ignored);
+                                      arithmetic stays fp32; requires COLVO_F_NO_SRC_GRAD in the backward
+                                                                        */
 
 /* negative error codes */
 #define COLVO_E_BAD_DESC (-1)
@@ -76,6 +79,7 @@ int colvo_saved_doubles(const ColvoDesc* d, size_t* count);
 
 /* Forward: SURVEY.md section 8(a) rows 0-10.
  *   tgt [B,3,H,W]  srcs [B,N,3,H,W]  depth[k] [B,1,h_k,w_k]  K [B,3,3]  T [B,N,4,4]
+ *   (with COLVO_F_PACKED_BF16: tgt [B,H,W,4] bf16, srcs [B,N,H,W,4] bf16, 8-byte aligned)
  *   src_depth [B,N,1,H,W]     (nullable) depth maps of the source frames: with geo_weight != 0 adds the
  *                             geometric-consistency term (README.md:1,7)
  *   loss  [1]                 (out)
@@ -84,7 +88,7 @@ int colvo_saved_doubles(const ColvoDesc* d, size_t* count);
  *   sel   [B,S,H,W]   u8      (out; required with COLVO_F_SAVE_FOR_BWD, else nullable)
  *   saved [colvo_saved_doubles] (out; required with COLVO_F_SAVE_FOR_BWD, else nullable)
  */
-int colvo_photo_forward(const ColvoDesc* d, const float* tgt, const float* srcs, const float* const* depth,
+int colvo_photo_forward(const ColvoDesc* d, const void* tgt, const void* srcs, const float* const* depth,
                         const float* K, const float* T, const float* src_depth, float* loss, float* ab,
                         uint8_t* valid, uint8_t* sel, double* saved, void* ws, size_t ws_bytes, void* stream);
 
@@ -96,7 +100,7 @@ int colvo_photo_forward(const ColvoDesc* d, const float* tgt, const float* srcs,
  *   grad_src_depth [B,N,1,H,W]    (out, overwritten; nullable)
  * No gradient is produced for K or tgt (oracle A14).
  */
-int colvo_photo_backward(const ColvoDesc* d, const float* tgt, const float* srcs, const float* const* depth,
+int colvo_photo_backward(const ColvoDesc* d, const void* tgt, const void* srcs, const float* const* depth,
                          const float* K, const float* T, const float* src_depth, const float* grad_loss,
                          const uint8_t* sel, const double* saved, float* const* grad_depth, float* grad_T,
                          float* grad_srcs, float* grad_src_depth, void* ws, size_t ws_bytes, void* stream);

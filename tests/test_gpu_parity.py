@@ -240,3 +240,37 @@ def test_geometric_consistency_term_parity(B, H, W, N, S):
     assert relinf(pose.grad[:, :, :3], op.grad[:, :, :3]) < TOL
     assert relinf(srcs.grad, osr.grad) < TOL
     assert relinf(sdg.grad, osd.grad) < TOL
+
+
+@pytest.mark.parametrize("B,H,W,N,S", [(2, 48, 64, 2, 4), (1, 37, 53, 1, 3)])
+def test_packed_bf16_image_storage_parity(B, H, W, N, S):
+    """images stored as RGBA bf16 (8 B/pixel), fp32 arithmetic.  The oracle runs on
+    the same quantised values widened to fp32, so the tolerances are the fp32 ones; only the inputs differ from
+    the fp32 storage case (|x - bf16(x)| <= 2^-9 per pixel value)."""
+    d = make_triplets(B, H, W, N=N, S=S, seed=43)
+    tgt_p, srcs_p = coivo_b200.pack_images(d["tgt"]), coivo_b200.pack_images(d["srcs"])
+    tgt_q, srcs_q = coivo_b200.unpack_images(tgt_p), coivo_b200.unpack_images(srcs_p)
+    assert (tgt_q - d["tgt"]).abs().max().item() <= 2.0 ** -8
+    depth = [x.to(DEV).requires_grad_() for x in d["depth"]]
+    pose = d["pose"].to(DEV).requires_grad_()
+    loss, valid, sel, ab = coivo_b200.photometric_loss(depth, pose, d["K"].to(DEV), tgt_p.to(DEV), srcs_p.to(DEV),
+                                                       return_masks=True)
+    loss.backward()
+    with torch.no_grad():
+        l0, v0, s0, ab0 = O.photometric_loss(d["depth"], d["pose"], d["K"], tgt_q, srcs_q, return_masks=True)
+        gap = O.candidate_gap(d["depth"], d["pose"], d["K"], tgt_q, srcs_q)
+    assert torch.equal(valid.cpu(), v0)
+    assert (gap[sel.cpu() != s0] < 1e-4).all()
+    assert abs(loss.item() - l0.item()) <= TOL * abs(l0.item())
+    assert torch.allclose(ab.cpu(), ab0, rtol=1e-5, atol=1e-6)
+    od = [x.clone().requires_grad_() for x in d["depth"]]
+    op = d["pose"].clone().requires_grad_()
+    O.photometric_loss(od, op, d["K"], tgt_q, srcs_q, sel_override=sel.cpu(), ab_override=ab.cpu()).backward()
+    for k in range(S):
+        assert relinf(depth[k].grad, od[k].grad) < TOL
+    assert relinf(pose.grad[:, :, :3], op.grad[:, :, :3]) < TOL
+    # and the same values through the planar fp32 path give the same loss
+    l_planar = coivo_b200.photometric_loss([x.detach() for x in depth], pose.detach(), d["K"].to(DEV), tgt_q.to(DEV), srcs_q.to(DEV))
+    assert abs(l_planar.item() - loss.item()) <= 1e-6 * abs(loss.item())
+    with pytest.raises(ValueError):
+        coivo_b200.photometric_loss(depth, pose, d["K"].to(DEV), tgt_p.to(DEV), srcs_p.to(DEV).requires_grad_())
