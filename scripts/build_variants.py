@@ -4,10 +4,12 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from coivo_b200 import _lib
 
 VARIANTS = {
-    "fs0_bs0": ["COLVO_FWD_SLOTS=0", "COLVO_BWD_SLOTS=0"],
-    "fs0_bs1": ["COLVO_FWD_SLOTS=0", "COLVO_BWD_SLOTS=1"],
-    "fs1_bs1": ["COLVO_FWD_SLOTS=1", "COLVO_BWD_SLOTS=1"],
-    "fs0_bs1_b2": ["COLVO_FWD_SLOTS=0", "COLVO_BWD_SLOTS=1", "COLVO_MINB_BWD=2"],
+    "base": [],
+    "f4": ["COLVO_MINB_FWD=4"],
+    "f2y": ["COLVO_MINB_FWD=2", "COLVO_Y_REGS=1"],
+    "s3": ["COLVO_MINB_STATS=3"],
+    "s5": ["COLVO_MINB_STATS=5"],
+    "b2": ["COLVO_MINB_BWD=2"],
 }
 out = os.path.join(os.path.dirname(_lib.PKG_DIR), "build", "variants")
 os.makedirs(out, exist_ok=True)
