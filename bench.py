@@ -138,6 +138,10 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: the path has no CPU fallback")
+    # keep stdout to the one JSON line: NCCL / torch banners written to fd 1 go to stderr until the end
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -220,9 +224,14 @@ def run_ours(args):
         g1.record()
         barrier()
         graph_ms = g0.elapsed_time(g1)
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(obj), flush=True)
+
     if args.profile:
         if rank == 0:
-            print(json.dumps({"profile_run": True, "ms_per_step": ms_total / steps, "kernel_ms": kern_ms}), flush=True)
+            emit({"profile_run": True, "ms_per_step": ms_total / steps, "kernel_ms": kern_ms})
         if world > 1:
             dist.destroy_process_group()
         return
@@ -293,7 +302,7 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": cpu_rate, "unit": UNIT, "cores": cpu_threads, "kind": "port",
                                     "sample": f"3 fwd+bwd passes of the full {B_PER_GPU}-triplet batch (oracle/photometric.py)",
                                     "ms_per_step": cpu_ms}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
