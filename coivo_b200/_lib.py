@@ -16,7 +16,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 # COLVO_LIB selects another build of the same sources (tuning experiments); the default is the in-tree library
 LIB_PATH = os.environ.get("COLVO_LIB") or os.path.join(PKG_DIR, "libcolvo_b200.so")
 SOURCES = ["colvo_fwd.cu", "colvo_bwd.cu", "colvo_api.cu", "colvo_front.cu"]
-HEADERS = ["colvo_math.cuh", "colvo_kernels.cuh", os.path.join("..", "..", "include", "colvo.h")]
+HEADERS = ["colvo_math.cuh", "colvo_kernels.cuh", "colvo_photo_fwd.cuh", os.path.join("..", "..", "include", "colvo.h")]
 
 # flags (include/colvo.h)
 F_LCC = 1

@@ -64,6 +64,8 @@ void fill_params(KP& P, const ColvoDesc* d) {
   P.K_bs = 9; P.T_ns = 16; P.T_bs = 16 * d->N;
   P.tiles_x = div_up(d->W, kTileW);
   P.tiles_y = div_up(d->H, kTileH);
+  P.ftiles_x = div_up(d->W, 32);
+  P.ftiles_y = div_up(d->H, kFwdTileH);
   for (int k = 0; k < d->S; ++k) {
     int c = div_up(d->h[k] * d->w[k], kSmoothPixPerBlock);
     P.sm_chunks[k] = c < 1 ? 1 : (c > kSmoothMaxChunks ? kSmoothMaxChunks : c);
@@ -82,7 +84,7 @@ size_t carve_fwd(const ColvoDesc* d, void* ws, FwdBuffers& F) {
   F.smooth_part = c.take<double>(BS * kSmoothMaxChunks * 3);
   F.loss_part = c.take<double>((size_t)d->B * tiles);
   F.g_part = c.take<double>((size_t)d->B * tiles * d->N * kMaxS * 2);
-  F.iw = c.take<float>(BNS * 3 * (size_t)d->H * d->W);
+  F.iw = c.take<float4>(BNS * (size_t)d->H * d->W);
   F.pyr[0] = nullptr;
   for (int k = 1; k < kMaxS; ++k) F.pyr[k] = (k < d->S) ? c.take<float>((size_t)d->B * 3 * d->h[k] * d->w[k]) : nullptr;
   return c.off;
@@ -118,6 +120,8 @@ size_t carve_saved(const ColvoDesc* d, double* saved, SavedView& sv) {
   if ((nd & 1) != 0) nf += 2;                  // ... also when the double count is odd
   sv.coef = f ? f + nf : nullptr;
   nf += (size_t)d->B * d->S * 12 * d->H * d->W;
+  sv.geo = f ? reinterpret_cast<float4*>(f + nf) : nullptr;
+  nf += BNS * 4 * (size_t)d->H * d->W;
   return nd + (nf + 1) / 2;
 }
 

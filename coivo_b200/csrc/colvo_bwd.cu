@@ -12,9 +12,6 @@
 //   k_pose_final     deterministic reduction of the pose-gradient partials
 #include "colvo_kernels.cuh"
 
-#ifndef COLVO_BWD_SLOTS     // 1: final pose reduction through smem slots; 0: fp64 shuffle trees
-#define COLVO_BWD_SLOTS 1
-#endif
 #ifndef COLVO_MINB_BWD      // CTAs per SM the register allocator must allow -- tuned on B200, see DESIGN.md
 #define COLVO_MINB_BWD 3
 #endif
@@ -31,26 +28,35 @@ __device__ __forceinline__ float smooth_grad(float s, float D, float inv, float 
 }
 
 // One CTA = one 32x8 tile of one triplet.  The SSIM adjoint coefficients of every window were
-// written by the forward (for the winning candidate), so the tile needs no halo re-warp: per scale
-// the CTA stages the coefficient tile (+1 halo) in shared memory, then every thread warps its own
-// pixel once per source, gathers the 3x3 neighbourhood of coefficients, and pushes the result
-// through the LCC, bilinear and projection adjoints.
+// written by the forward (for the winning candidate, zeros where an identity candidate won; .w = index
+// of the winning source), and k_warp_stats saved the projection (u', v', iz, D^|valid) of every pixel,
+// so the tile needs neither a halo re-warp nor a re-projection: per scale the CTA stages the
+// coefficient tile (+1 halo) in shared memory, every thread gathers its 3x3 neighbourhood, samples
+// the four taps of each source at the saved coordinates, and pushes the result through the LCC,
+// bilinear and projection adjoints.
+struct BwdConst {          // per warped frame (n, k), built once per CTA
+  float a, b;              // LCC gain / bias
+  float l0, ly, lx;        // LCC adjoint of a valid sample: l0 + ly * y + lx * x
+  float wl1;               // weight of the L1 term's sign at the own pixel: wscale * (1 - alpha) / 3 * a
+  float pad0, pad1;
+};
+
 template <int NS, bool GEO, bool PK>
 __global__ void __launch_bounds__(kThreads, COLVO_MINB_BWD)
     k_photo_bwd(KP P, const float* __restrict__ grad_loss, const uint8_t* __restrict__ sel,
                 const double* __restrict__ saved_frame, const double* __restrict__ saved_scale,
-                const float* __restrict__ s_field0, const float* __restrict__ coef_in, float* __restrict__ grad_d0,
+                const float* __restrict__ s_field0, const float* __restrict__ coef_in,
+                const float4* __restrict__ geo_in, float* __restrict__ grad_d0,
                 float* __restrict__ dD1, float* __restrict__ dD2, float* __restrict__ dD3,
                 float* __restrict__ grad_srcs, float* __restrict__ grad_src_depth, double* __restrict__ pose_part) {
   // dynamic shared memory, carved by hand
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float4 (*coef)[kCN * 3] = reinterpret_cast<float4 (*)[kCN * 3]>(smem_raw);   // [2]: (ca, cb, cg, -) per window
+  float4 (*coef)[kCN * 3] = reinterpret_cast<float4 (*)[kCN * 3]>(smem_raw);   // [2]: (ca, cb, cg, n) per window
                                                                                // centre and channel, double-buffered over k
   double* red = reinterpret_cast<double*>(smem_raw + sizeof(float4) * 2 * kCN * 3);
-  float (*cst)[kMaxS][6] = reinterpret_cast<float (*)[kMaxS][6]>(red + (kThreads / 32) * NS * 12);
-                                                    // [NS]: a, b, P, Q, mean_x, mean_y per warped frame
-  float* cst_sm = reinterpret_cast<float*>(cst + NS);   // scale 0: 1/(mean+eps), sum(s d)/(n (mean+eps)^2)
-  unsigned char (*sels)[kCN] = reinterpret_cast<unsigned char (*)[kCN]>(cst_sm + 2);   // [kMaxS]
+  BwdConst (*cst)[kMaxS] = reinterpret_cast<BwdConst (*)[kMaxS]>(red + (kThreads / 32) * NS * 12);   // [NS][kMaxS]
+  float (*pose_s)[12] = reinterpret_cast<float (*)[12]>(cst + NS);                                   // [NS]: R row-major, t
+  float* cst_sm = reinterpret_cast<float*>(pose_s + NS);   // scale 0: 1/(mean+eps), sum(s d)/(n (mean+eps)^2)
 
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
   const int b = blockIdx.z, x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
@@ -63,29 +69,32 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_BWD)
   const float go = __ldg(grad_loss);
   const float wscale = go / ((float)P.S * (float)P.B * (float)P.HW);
 
-  // ---- phase 0: selection masks (+1 halo), per-frame constants ----
-  for (int idx = tid; idx < kCN; idx += kThreads) {
-    int r = idx / kCW, c = idx - r * kCW;
-    int gy = y0 - 1 + r, gx = x0 - 1 + c;
-    bool inside = gy >= 0 && gy < P.H && gx >= 0 && gx < P.W;
-    for (int k = 0; k < P.S; ++k)
-      sels[k][idx] = inside ? sel[((long long)b * P.S + k) * P.HW + gy * P.W + gx] : (unsigned char)255;
-  }
+  // ---- phase 0: per-frame constants ----
   if (tid < NS * kMaxS) {
-    int n = tid / kMaxS, k = tid % kMaxS;
-    float a = 1.f, bb = 0.f, Pc = 0.f, Qc = 0.f, mx = 0.f, my = 0.f;
+    const int n = tid / kMaxS, k = tid % kMaxS;
+    BwdConst c;
+    c.a = 1.f; c.b = 0.f; c.l0 = c.ly = c.lx = 0.f; c.pad0 = c.pad1 = 0.f;
     if (k < P.S) {
       const double* s = saved_frame + ((long long)(b * P.N + n) * P.S + k) * kSavedPerFrame;
-      a = (float)s[4];
-      bb = (float)s[5];
-      mx = (float)s[1];
-      my = (float)s[2];
+      c.a = (float)s[4];
+      c.b = (float)s[5];
       if ((P.flags & 1u) && !(P.flags & 2u) && s[0] > 0.0) {
-        Pc = (float)((double)go * (s[6] - s[7] * s[1]) * s[3]);
-        Qc = (float)((double)go * s[7] * s[4] / s[0]);
+        // lcc_q = Pc * ((y - my) - 2 a (x - mx)) - Qc   (SURVEY.md appendix A), expanded in y and x
+        const double Pc = (double)go * (s[6] - s[7] * s[1]) * s[3];
+        const double Qc = (double)go * s[7] * s[4] / s[0];
+        const double a = s[4];
+        c.ly = (float)Pc;
+        c.lx = (float)(-2.0 * a * Pc);
+        c.l0 = (float)(-Pc * s[2] + 2.0 * a * Pc * s[1] - Qc);
       }
     }
-    cst[n][k][0] = a; cst[n][k][1] = bb; cst[n][k][2] = Pc; cst[n][k][3] = Qc; cst[n][k][4] = mx; cst[n][k][5] = my;
+    c.wl1 = wscale * (1.f - P.alpha) * (1.0f / 3.0f) * c.a;
+    cst[n][k] = c;
+  }
+  if (tid >= 32 && tid < 32 + NS * 12) {
+    const int n = (tid - 32) / 12, j = (tid - 32) % 12;
+    const float* t = P.T + (long long)b * P.T_bs + (long long)n * P.T_ns;
+    pose_s[n][j] = (j < 9) ? __ldg(t + 4 * (j / 3) + (j % 3)) : __ldg(t + 4 * (j - 9) + 3);
   }
   if (tid == 64) {
     const double* sc = saved_scale + (long long)(b * P.S) * kSavedPerScale;
@@ -94,11 +103,11 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_BWD)
     cst_sm[1] = (float)(sc[1] / ((double)P.HW * me * me));
   }
 
-  // reflect-padding multiplicities of the 3x3 gather at the own pixel (per axis)
+  // reflect-padding multiplicities of the 3x3 gather at the own pixel (per axis); the loss weight rides on the rows
   float my3[3], mx3[3];
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
-    my3[d] = reflect_mult(py, py + d - 1, P.H);
+    my3[d] = wscale * reflect_mult(py, py + d - 1, P.H);
     mx3[d] = reflect_mult(px, px + d - 1, P.W);
   }
   float yq[3];
@@ -112,20 +121,19 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_BWD)
   for (int n = 0; n < NS; ++n)
 #pragma unroll
     for (int i = 0; i < 3; ++i) pw[n][i] = pt[n][i] = 0.f;
-  __syncthreads();                                   // sels, cst visible
 
-  // Coefficient tile of scale k (+1 halo; zeros where no re-projection won or outside the image), fetched with
-  // cp.async one scale ahead so its global latency hides behind the previous scale's arithmetic.
+  // Coefficient tile of scale k (+1 halo; zeros outside the image), fetched with cp.async one scale ahead so its
+  // global latency hides behind the previous scale's arithmetic.
   auto stage_coef = [&](int k) {
     float4* cbf = coef[k & 1];
     const float4* cin = reinterpret_cast<const float4*>(coef_in) + (long long)(b * P.S + k) * P.HW * 3;
     for (int idx = tid; idx < kCN; idx += kThreads) {
       const int r = idx / kCW, c = idx - r * kCW;
-      const unsigned char sv = sels[k][idx];
-      const bool on = sv != 255 && sv >= NS;
-      const float4* p = on ? cin + ((y0 - 1 + r) * P.W + (x0 - 1 + c)) * 3 : cin;
+      const int gy = y0 - 1 + r, gx = x0 - 1 + c;
+      const bool on = gy >= 0 && gy < P.H && gx >= 0 && gx < P.W;
+      const float4* p = on ? cin + (gy * P.W + gx) : cin;
 #pragma unroll
-      for (int ch = 0; ch < 3; ++ch) cp_async16(cbf + idx * 3 + ch, p + ch, on);
+      for (int ch = 0; ch < 3; ++ch) cp_async16(cbf + idx * 3 + ch, p + (long long)ch * P.HW, on);
     }
     cp_async_commit();
   };
@@ -134,14 +142,18 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_BWD)
 #pragma unroll 1
   for (int k = 0; k < P.S; ++k) {
     const float4* cb = coef[k & 1];
-    const float* Dk = P.depth[k] + (long long)b * P.depth_bs[k];
-    const float D_own = depth_at(P, Dk, k, qx, qy);
+    // projection of the own pixel into both sources, and which candidate won here
+    float4 gt[NS];
+#pragma unroll
+    for (int n = 0; n < NS; ++n) gt[n] = __ldg(geo_in + (long long)((b * P.N + n) * P.S + k) * P.HW + qo);
+    const int own_sel = __ldg(sel + ((long long)b * P.S + k) * P.HW + qo);
     cp_async_wait_all();
-    __syncthreads();   // scale k landed for every thread, and everyone is done reading the other buffer
+    __syncthreads();   // scale k landed for every thread (first pass: constants visible), nobody reads the other buffer
     if (k + 1 < P.S) stage_coef(k + 1);
     float dD = 0.f;
-    // gather once per scale: every window centre has at most one winning source, so its coefficients go to
-    // that source's accumulators (one pass over the 3x3 neighbourhood serves both sources)
+    // gather once per scale: every window centre has at most one winning source (texel .w = its index), so its
+    // coefficients go to that source's accumulators (one pass over the 3x3 neighbourhood serves both sources;
+    // exact zeros for the other source -- the three sums cancel heavily against each other downstream)
     float A[NS][3], Bc[NS][3], G[NS][3];
 #pragma unroll
     for (int n = 0; n < NS; ++n)
@@ -151,14 +163,16 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_BWD)
 #pragma unroll
       for (int j = 0; j < 9; ++j) {
         const int o = oc + (j / 3) * kCW + (j % 3);
-        const unsigned char sv = sels[k][o];
         const float m = my3[j / 3] * mx3[j % 3];
         float mn[NS];
 #pragma unroll
-        for (int n = 0; n < NS; ++n) mn[n] = (sv == (unsigned char)(NS + n)) ? m : 0.f;
-#pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
           const float4 q = cb[o * 3 + ch];
+          if (ch == 0) {
+            mn[NS - 1] = m * q.w;                       // q.w is 0 or 1
+            if (NS > 1) mn[0] = m - mn[NS - 1];
+            else mn[0] = m;
+          }
 #pragma unroll
           for (int n = 0; n < NS; ++n) {
             A[n][ch] = fmaf(mn[n], q.x, A[n][ch]);
@@ -168,35 +182,49 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_BWD)
         }
       }
     }
+    const float D_own = gt[0].w;
 #pragma unroll
     for (int n = 0; n < NS; ++n) {
       if (in_img) {
         const Img<PK> src = img_at<PK>(P, P.srcs, b * P.src_bf + n * P.src_nf);
-        const Pose pose = load_pose(P, b, n);
-        const float a = cst[n][k][0], bb = cst[n][k][1];
-        const float Pc = cst[n][k][2], Qc = cst[n][k][3], mx = cst[n][k][4], my = cst[n][k][5];
-        Geo g; Taps t; Texels tx4; float xq[3];
-        warp_sample<PK>(P, src, cam, pose, own_rx, own_ry, D_own, g, t, tx4, xq);
-        const float wq = (sels[k][oc + kCW + 1] == (unsigned char)(NS + n)) ? wscale * (1.f - P.alpha) * (1.0f / 3.0f) : 0.f;
-        float hq[3];
+        Pose pose;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) pose.r[i] = pose_s[n][i];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) pose.t[i] = pose_s[n][9 + i];
+        const BwdConst c = cst[n][k];
+        Geo g;
+        g.u = gt[n].x; g.v = gt[n].y; g.iz = gt[n].z; g.rx = own_rx; g.ry = own_ry;
+        g.valid = (__float_as_uint(gt[n].w) & 1u) != 0u;
+        const Taps t = make_taps(g.u, g.v, P.W, P.H);
+        Texels tx4;
+        const int r0 = t.y0 * P.W, r1 = t.y1 * P.W;
+        src.load_taps(r0 + t.x0, r0 + t.x1, r1 + t.x0, r1 + t.x1, tx4);
+        const float wl1 = (own_sel == NS + n) ? c.wl1 : 0.f;
+        float du = 0.f, dv = 0.f, hq[3];
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
-          float gq = wscale * (A[n][ch] + xq[ch] * Bc[n][ch] + yq[ch] * G[n][ch]) + wq * a * sgn(fmaf(a, xq[ch], bb) - yq[ch]);
-          float lcc = g.valid ? (Pc * ((yq[ch] - my) - 2.f * a * (xq[ch] - mx)) - Qc) : 0.f;
-          hq[ch] = gq + lcc;
+          // bilinear sample and its coordinate derivatives from one cross term
+          const float d01 = tx4.i01[ch] - tx4.i00[ch], e10 = tx4.i10[ch] - tx4.i00[ch];
+          const float cross = (tx4.i11[ch] - tx4.i10[ch]) - d01;
+          const float dux = fmaf(t.wy, cross, d01), dvy = fmaf(t.wx, cross, e10);
+          const float xq = fmaf(t.wy, dvy, fmaf(t.wx, d01, tx4.i00[ch]));
+          const float diff = fmaf(c.a, xq, c.b) - yq[ch];
+          float h = fmaf(xq, Bc[n][ch], fmaf(yq[ch], G[n][ch], A[n][ch]));
+          h = fmaf(wl1, sgn(diff), h);
+          const float lcc = fmaf(c.lx, xq, fmaf(c.ly, yq[ch], c.l0));
+          h += g.valid ? lcc : 0.f;
+          hq[ch] = h;
+          du = fmaf(h, dux, du);
+          dv = fmaf(h, dvy, dv);
         }
-        float du = 0.f, dv = 0.f;
-        const float w00 = (1.f - t.wx) * (1.f - t.wy), w01 = t.wx * (1.f - t.wy);
-        const float w10 = (1.f - t.wx) * t.wy, w11 = t.wx * t.wy;
-        // (grad_srcs is planar fp32 [B,N,3,H,W]; it is null for packed sources: quantised images carry no gradient)
-        float* gs = grad_srcs ? grad_srcs + (b * P.src_bf + n * P.src_nf) * (3ll * P.HW) : nullptr;
-        float *g00 = gs + (t.y0 * P.W + t.x0), *g01 = gs + (t.y0 * P.W + t.x1);
-        float *g10 = gs + (t.y1 * P.W + t.x0), *g11 = gs + (t.y1 * P.W + t.x1);
+        if (grad_srcs) {
+          // (grad_srcs is planar fp32 [B,N,3,H,W]; it is null for packed sources: quantised images carry no gradient)
+          const float w11 = t.wx * t.wy, w01 = t.wx - w11, w10 = t.wy - w11, w00 = 1.f - t.wx - w10;
+          float* gs = grad_srcs + (b * P.src_bf + n * P.src_nf) * (3ll * P.HW);
+          float *g00 = gs + (r0 + t.x0), *g01 = gs + (r0 + t.x1), *g10 = gs + (r1 + t.x0), *g11 = gs + (r1 + t.x1);
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-          du += hq[ch] * ((1.f - t.wy) * (tx4.i01[ch] - tx4.i00[ch]) + t.wy * (tx4.i11[ch] - tx4.i10[ch]));
-          dv += hq[ch] * ((1.f - t.wx) * (tx4.i10[ch] - tx4.i00[ch]) + t.wx * (tx4.i11[ch] - tx4.i01[ch]));
-          if (gs) {
+          for (int ch = 0; ch < 3; ++ch) {
             atomicAdd(g00, w00 * hq[ch]);
             atomicAdd(g01, w01 * hq[ch]);
             atomicAdd(g10, w10 * hq[ch]);
@@ -210,18 +238,19 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_BWD)
         if (GEO && g.valid) {
           float d4[4], dZ, dS;
           const float ds = sample_plane(P.src_depth + (long long)(b * P.N + n) * P.HW, t, P.W, d4);
-          geo_diff(g.Zp, ds, dZ, dS);
+          geo_diff(p_sub(p_rcp(g.iz), P.eps_proj), ds, dZ, dS);     // Z' back from iz = 1 / (Z' + eps)
           const float wg = go * P.geo_weight / ((float)P.S * (float)P.B * (float)P.N * (float)P.HW);
           dZp_direct = wg * dZ;
           const float gS = wg * dS;
           du += gS * ((1.f - t.wy) * (d4[1] - d4[0]) + t.wy * (d4[3] - d4[2]));
           dv += gS * ((1.f - t.wx) * (d4[2] - d4[0]) + t.wx * (d4[3] - d4[1]));
           if (grad_src_depth) {
+            const float w11 = t.wx * t.wy, w01 = t.wx - w11, w10 = t.wy - w11, w00 = 1.f - t.wx - w10;
             float* gd = grad_src_depth + (long long)(b * P.N + n) * P.HW;
-            atomicAdd(gd + (t.y0 * P.W + t.x0), w00 * gS);
-            atomicAdd(gd + (t.y0 * P.W + t.x1), w01 * gS);
-            atomicAdd(gd + (t.y1 * P.W + t.x0), w10 * gS);
-            atomicAdd(gd + (t.y1 * P.W + t.x1), w11 * gS);
+            atomicAdd(gd + (r0 + t.x0), w00 * gS);
+            atomicAdd(gd + (r0 + t.x1), w01 * gS);
+            atomicAdd(gd + (r1 + t.x0), w10 * gS);
+            atomicAdd(gd + (r1 + t.x1), w11 * gS);
           }
         }
         if (!t.gx) du = 0.f;
@@ -249,7 +278,6 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_BWD)
 
   // ---- per-tile pose-gradient partials (fp64: sums of terms of both signs) ----
   const int blk = (b * P.tiles_y + blockIdx.y) * P.tiles_x + blockIdx.x;
-#if COLVO_BWD_SLOTS
   __syncthreads();                                   // the coefficient buffers are free: reuse them as slot storage
   float* slots = reinterpret_cast<float*>(smem_raw); // [NS*12][kThreads] <= 24 KB of the 32 KB coefficient area
 #pragma unroll
@@ -261,26 +289,6 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_BWD)
   }
   __syncthreads();
   block_sum_slots<NS * 12>(slots, red, [&](int slot, double v) { pose_part[(long long)blk * (NS * 12) + slot] = v; });
-#else
-  const int lane = tid & 31, wid = tid >> 5;
-#pragma unroll
-  for (int n = 0; n < NS; ++n) {
-    float gp[12];
-    pose_grad_expand(pw[n], pt[n], own_rx, own_ry, gp);
-#pragma unroll
-    for (int j = 0; j < 12; ++j) {
-      double s = warp_sum(in_img ? (double)gp[j] : 0.0);
-      if (lane == 0) red[wid * (NS * 12) + n * 12 + j] = s;
-    }
-  }
-  __syncthreads();
-  if (tid < NS * 12) {
-    double s = 0.0;
-#pragma unroll
-    for (int w = 0; w < kThreads / 32; ++w) s += red[w * (NS * 12) + tid];
-    pose_part[(long long)blk * (NS * 12) + tid] = s;
-  }
-#endif
 }
 
 // ------------------------------------------------------------------------------------------
@@ -379,7 +387,7 @@ static inline int div_up(int a, int b) { return (a + b - 1) / b; }
 template <int NS>
 static size_t photo_bwd_smem() {
   return sizeof(float4) * 2 * kCN * 3 + sizeof(double) * (kThreads / 32) * NS * 12 +
-         sizeof(float) * NS * kMaxS * 6 + sizeof(float) * 2 + kMaxS * kCN;
+         sizeof(BwdConst) * NS * kMaxS + sizeof(float) * NS * 12 + sizeof(float) * 2;
 }
 
 cudaError_t launch_backward(const KP& P, const BwdBuffers& Wk, const float* grad_loss, const uint8_t* sel,
@@ -400,7 +408,7 @@ cudaError_t launch_backward(const KP& P, const BwdBuffers& Wk, const float* grad
     // opting in to > 48 KB of dynamic shared memory is a per-function, per-device attribute: cheap and idempotent
     auto launch = [&](auto kern, size_t smem) {
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      kern<<<grid, kThreads, smem, st>>>(P, grad_loss, sel, sv.frame, sv.scale, sv.s_field[0], sv.coef, grad_depth[0],
+      kern<<<grid, kThreads, smem, st>>>(P, grad_loss, sel, sv.frame, sv.scale, sv.s_field[0], sv.coef, sv.geo, grad_depth[0],
                                          Wk.dDhat[1], Wk.dDhat[2], Wk.dDhat[3], grad_srcs, grad_src_depth, Wk.pose_part);
     };
     const bool geo = P.src_depth != nullptr, pk = (P.flags & 16u) != 0;

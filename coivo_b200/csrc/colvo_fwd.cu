@@ -9,16 +9,11 @@
 //   k_smooth_fwd    edge-aware smoothness partials (+ its adjoint field when saving)  (row 9)
 //   k_finalize_fwd  deterministic final sums -> loss, G_a, G_b, sum s*d               (row 10)
 #include "colvo_kernels.cuh"
+#include "colvo_photo_fwd.cuh"
 
 // occupancy knobs (CTAs per SM the register allocator must allow) -- tuned on B200, see DESIGN.md
-#ifndef COLVO_MINB_FWD
-#define COLVO_MINB_FWD 3
-#endif
 #ifndef COLVO_MINB_STATS
 #define COLVO_MINB_STATS 4
-#endif
-#ifndef COLVO_FWD_SLOTS     // 1: park dL/da, dL/db terms in smem slots and sum once; 0: fp64 shuffle tree per scale
-#define COLVO_FWD_SLOTS 0
 #endif
 #ifndef COLVO_Y_REGS        // 1: keep the 3x3 target window of the own pixel in registers (27 regs)
 #define COLVO_Y_REGS 0
@@ -103,7 +98,8 @@ __global__ void __launch_bounds__(kThreads)
 // costs more issue slots than the 12 B/pixel round trip costs bandwidth on this ALU-bound path.
 template <int NS, bool GEO, bool PK>
 __global__ void __launch_bounds__(kThreads, COLVO_MINB_STATS)
-    k_warp_stats(KP P, double* __restrict__ part, uint8_t* __restrict__ valid_out, float* __restrict__ iw_out) {
+    k_warp_stats(KP P, double* __restrict__ part, uint8_t* __restrict__ valid_out, float4* __restrict__ iw_out,
+                 float4* __restrict__ geo_out) {
   constexpr int NA = GEO ? kStatVals : 5;      // accumulators per source (the 6th only with the geometric term)
   constexpr int NV = NA * NS;
   __shared__ double sm[(kThreads / 32) * NV];
@@ -140,12 +136,12 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_STATS)
         warp_sample<PK>(P, src, cam, pose[n], rx, ry, D, g, t, tx, x);
         const int bnk = (b * P.N + n) * P.S + k;
         if (valid_out) valid_out[(long long)bnk * P.HW + pix] = g.valid ? 1 : 0;
-        if (iw_out) {          // raw warped frame, re-used by k_photo_fwd instead of warping again (+halo)
-          float* o = iw_out + (long long)bnk * 3 * P.HW + pix;
-          o[0] = x[0];
-          o[P.HW] = x[1];
-          o[2 * (long long)P.HW] = x[2];
-        }
+        // raw warped frame, re-used by k_photo_fwd instead of warping again (+halo): one 16-byte texel
+        if (iw_out) iw_out[(long long)bnk * P.HW + pix] = make_float4(x[0], x[1], x[2], 0.f);
+        // the projection itself, for the backward (valid rides in the mantissa LSB of the depth)
+        if (geo_out)
+          geo_out[(long long)bnk * P.HW + pix] =
+              make_float4(g.u, g.v, g.iz, __uint_as_float((__float_as_uint(D) & ~1u) | (g.valid ? 1u : 0u)));
         if (g.valid) {
           acc[NA * n + 0] += 3.0;
           acc[NA * n + 1] += (double)(x[0] + x[1] + x[2]);
@@ -217,11 +213,9 @@ __global__ void __launch_bounds__(32)
 }
 
 // ------------------------------------------------------------------------------------------
-// The fused tile kernel.  One CTA = one 32x8 output tile of one triplet; the (k, n) loops run
-// inside the CTA so the target tile, its SSIM moments and the identity candidates are computed
-// once and shared by all 2*S warped frames.  The warped tile (+1 halo, read from the frames
-// k_warp_stats left in scratch) is double-buffered in shared memory and fetched one frame ahead with
-// cp.async: one __syncthreads per frame, global latency hidden behind the previous frame's SSIM.
+// 3x3-window helpers of the consistency sweep's tile kernel (k_consistency_pe below): one window per
+// thread over a 32x8 tile (+1 halo) in shared memory.  The training loss uses the strip kernel in
+// colvo_photo_fwd.cuh instead.
 constexpr int kFH = kTileH + 2, kFW = kTileW + 2;   // tile + 1-pixel SSIM halo
 constexpr int kFN = kFH * kFW;
 
@@ -285,198 +279,6 @@ __device__ __forceinline__ void ywin_init(YWin& y, const float* ys, int own) {
     y.mu[c] = s * (1.0f / 9.0f);
     y.sg[c] = ss * (1.0f / 9.0f) - y.mu[c] * y.mu[c];
   }
-}
-
-template <int NS, bool PK>
-__global__ void __launch_bounds__(kThreads, COLVO_MINB_FWD)
-    k_photo_fwd(KP P, const float* __restrict__ ab, uint8_t* __restrict__ sel_out, double* __restrict__ loss_part,
-                double* __restrict__ g_part, int need_g, float* __restrict__ coef_out, const float* __restrict__ iw) {
-  constexpr int NV = 1 + NS * kMaxS * 2;
-  __shared__ float ys[3 * kFN];
-  __shared__ float xs[2][3 * kFN];
-#if COLVO_FWD_SLOTS
-  __shared__ float slots[NV * kThreads];            // per-thread loss / dL/da / dL/db terms, summed once at the end
-#endif
-  __shared__ double red[(kThreads / 32) * NV];
-
-  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
-  const int b = blockIdx.z, x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
-  const int px = x0 + tx, py = y0 + ty;
-  const bool in_img = (px < P.W) && (py < P.H);
-  const int own = ty * kFW + tx;
-  const Img<PK> tg = img_at<PK>(P, P.tgt, b * P.tgt_bf);
-
-  // the (at most) two halo-tile positions this thread fills for every frame (reflect-padded coordinates)
-  int pso[2], pgo[2];
-  bool pok[2];
-#pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    const int idx = tid + j * kThreads;
-    pok[j] = idx < kFN;
-    const int r = idx / kFW, c = idx - r * kFW;
-    pso[j] = idx;
-    pgo[j] = reflect_clamp(y0 - 1 + r, P.H) * P.W + reflect_clamp(x0 - 1 + c, P.W);
-  }
-  // Frame sequence of this tile: f < NS the raw sources (identity candidates), then f = NS + k*NS + n the
-  // warped frames.  Frame f+1 is fetched with cp.async into the other buffer while frame f is evaluated.
-  auto stage = [&](int f) {
-    float* xb = xs[f & 1];
-    if (PK && f < NS) {   // packed bf16 sources are widened on the way in: plain loads (2 of the 2 + 2S frames)
-      const Img<PK> im = img_at<PK>(P, P.srcs, b * P.src_bf + f * P.src_nf);
-#pragma unroll
-      for (int j = 0; j < 2; ++j)
-        if (pok[j]) {
-          float v[3];
-          im.load3(pgo[j], v);
-#pragma unroll
-          for (int ch = 0; ch < 3; ++ch) xb[ch * kFN + pso[j]] = v[ch];
-        }
-      cp_async_commit();   // (empty group: keeps the wait/commit pairing uniform)
-      return;
-    }
-    const float* p;
-    if (f < NS) {
-      p = static_cast<const float*>(P.srcs) + (b * P.src_bf + f * P.src_nf) * P.frame_el;
-    } else {
-      const int k = (f - NS) / NS, n = (f - NS) % NS;
-      p = iw + (long long)((b * P.N + n) * P.S + k) * 3 * P.HW;
-    }
-#pragma unroll
-    for (int j = 0; j < 2; ++j)
-      if (pok[j]) {
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) cp_async4(xb + ch * kFN + pso[j], p + (ch * P.HW + pgo[j]), true);
-      }
-    cp_async_commit();
-  };
-  const int n_frames = NS + P.S * NS;
-  stage(0);
-#pragma unroll
-  for (int j = 0; j < 2; ++j)
-    if (pok[j]) {
-      float v[3];
-      tg.load3(pgo[j], v);
-#pragma unroll
-      for (int ch = 0; ch < 3; ++ch) ys[ch * kFN + pso[j]] = v[ch];
-    }
-  __syncthreads();
-
-  YWin yw;
-  ywin_init(yw, ys, own);
-
-  // identity candidates: raw sources, no calibration (oracle A10)
-  float ident[NS];
-#pragma unroll
-  for (int n = 0; n < NS; ++n) {
-    const float* xb = xs[n & 1];
-    cp_async_wait_all();
-    __syncthreads();              // frame n landed everywhere; everyone is done with the other buffer
-    if (n + 1 < n_frames) stage(n + 1);
-    ident[n] = in_img ? pe_own(xb, yw, 1.0f, 0.0f, P) : 0.f;
-  }
-
-  float loss_acc = 0.f;
-#if COLVO_FWD_SLOTS
-  if (need_g) {
-#pragma unroll
-    for (int i = 1; i < NV; ++i) slots[i * kThreads + tid] = 0.f;            // slots of unused scales stay 0
-  }
-#else
-  const int lane = tid & 31, wid = tid >> 5;
-  for (int i = tid; i < (kThreads / 32) * NV; i += kThreads) red[i] = 0.0;   // slots of unused scales stay 0
-#endif
-
-#pragma unroll
-  for (int k = 0; k < kMaxS; ++k) {
-    if (k < P.S) {
-      float best = ident[0];
-      int sel = 0;
-#pragma unroll
-      for (int n = 1; n < NS; ++n)
-        if (ident[n] < best) { best = ident[n]; sel = n; }
-      float dpa[NS], dpb[NS];
-      Coef cf[NS][3];          // unit-weight SSIM adjoint coefficients of candidate n, until the winner is known
-#pragma unroll
-      for (int n = 0; n < NS; ++n) {
-        const int bnk = (b * P.N + n) * P.S + k;
-        const float a = __ldg(ab + 2 * bnk), bb = __ldg(ab + 2 * bnk + 1);
-        const int f = NS + k * NS + n;
-        const float* xb = xs[f & 1];
-        cp_async_wait_all();
-        __syncthreads();          // frame f landed everywhere; everyone is done with the other buffer
-        if (f + 1 < n_frames) stage(f + 1);
-        dpa[n] = 0.f;
-        dpb[n] = 0.f;
-        if (in_img) {
-          float pe = pe_own(xb, yw, a, bb, P, need_g ? &dpa[n] : nullptr, need_g ? &dpb[n] : nullptr,
-                            coef_out != nullptr, cf[n]);
-          if (pe < best) { best = pe; sel = NS + n; }
-        }
-      }
-      if (in_img) {
-        loss_acc += best;
-        if (sel_out) sel_out[((long long)b * P.S + k) * P.HW + py * P.W + px] = (uint8_t)sel;
-#pragma unroll
-        for (int n = 0; n < NS; ++n) {
-          if (sel == NS + n) {
-            if (coef_out) {     // the backward reads these only where sel says a re-projection won
-              float4* co = reinterpret_cast<float4*>(coef_out) + ((long long)(b * P.S + k) * P.HW + py * P.W + px) * 3;
-#pragma unroll
-              for (int ch = 0; ch < 3; ++ch) co[ch] = make_float4(cf[n][ch].ca, cf[n][ch].cb, cf[n][ch].cg, 0.f);
-            }
-          }
-        }
-      }
-      // dL/da, dL/db terms of this scale: parked in shared memory (own slot per thread, no accumulator
-      // registers); summed in fp64 at the end -- they are large terms of both signs
-      if (need_g) {
-#pragma unroll
-        for (int n = 0; n < NS; ++n) {
-          const bool w = in_img && sel == NS + n;
-#if COLVO_FWD_SLOTS
-          slots[(1 + (n * kMaxS + k) * 2 + 0) * kThreads + tid] = w ? dpa[n] * (1.0f / 3.0f) : 0.f;
-          slots[(1 + (n * kMaxS + k) * 2 + 1) * kThreads + tid] = w ? dpb[n] * (1.0f / 3.0f) : 0.f;
-#else
-          // reduce in fp64 right away: each slot is written exactly once per warp, no accumulator registers
-          double sa = warp_sum(w ? (double)(dpa[n] * (1.0f / 3.0f)) : 0.0);
-          double sb = warp_sum(w ? (double)(dpb[n] * (1.0f / 3.0f)) : 0.0);
-          if (lane == 0) {
-            red[wid * NV + 1 + (n * kMaxS + k) * 2 + 0] = sa;
-            red[wid * NV + 1 + (n * kMaxS + k) * 2 + 1] = sb;
-          }
-#endif
-        }
-      }
-    }
-  }
-
-  // Per-tile partials: slot 0 = loss, slots 1.. = dL/da, dL/db per warped frame.
-  const int blk = (b * P.tiles_y + blockIdx.y) * P.tiles_x + blockIdx.x;
-#if COLVO_FWD_SLOTS
-  slots[tid] = loss_acc;
-  __syncthreads();
-  if (need_g) {
-    block_sum_slots<NV>(slots, red, [&](int slot, double v) {
-      if (slot == 0) loss_part[blk] = v;
-      else g_part[(long long)blk * (NS * kMaxS * 2) + (slot - 1)] = v;
-    });
-  } else {
-    block_sum_slots<1>(slots, red, [&](int, double v) { loss_part[blk] = v; });
-  }
-#else
-  {
-    double s = warp_sum((double)loss_acc);
-    if (lane == 0) red[wid * NV] = s;
-  }
-  __syncthreads();
-  if (tid < NV && (tid == 0 || need_g)) {
-    double s = 0.0;
-#pragma unroll
-    for (int w = 0; w < kThreads / 32; ++w) s += red[w * NV + tid];
-    if (tid == 0) loss_part[blk] = s;
-    else g_part[(long long)blk * (NS * kMaxS * 2) + (tid - 1)] = s;
-  }
-#endif
 }
 
 // ------------------------------------------------------------------------------------------
@@ -565,7 +367,7 @@ __global__ void __launch_bounds__(kThreads)
                    int need_g) {
   __shared__ double sm[(kThreads / 32) * 2];
   __shared__ double wk_s[kMaxS][2];
-  const int tiles = P.tiles_x * P.tiles_y;
+  const int tiles = P.ftiles_x * P.ftiles_y;    // k_photo_fwd's tiling
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int BNS = P.B * P.N * P.S;
   if (blockIdx.x == 0) {
@@ -734,7 +536,7 @@ cudaError_t launch_forward(const KP& P, const FwdBuffers& Wk, float* loss, float
     ScopedKernelTimer tm(3, st);
     dim3 g(Wk.stat_chunks, P.B * P.S);
     const bool geo = P.src_depth != nullptr;
-    auto run = [&](auto kern) { kern<<<g, kThreads, 0, st>>>(P, Wk.stat_part, valid, Wk.iw); };
+    auto run = [&](auto kern) { kern<<<g, kThreads, 0, st>>>(P, Wk.stat_part, valid, Wk.iw, save ? sv.geo : nullptr); };
     if (P.N == 1) {
       if (geo) { if (pk) run(k_warp_stats<1, true, true>); else run(k_warp_stats<1, true, false>); }
       else { if (pk) run(k_warp_stats<1, false, true>); else run(k_warp_stats<1, false, false>); }
@@ -744,13 +546,17 @@ cudaError_t launch_forward(const KP& P, const FwdBuffers& Wk, float* loss, float
     }
   }
   k_lcc_solve<<<BNS, 32, 0, st>>>(P, Wk.stat_part, Wk.stat_chunks, ab, save ? sv.frame : nullptr);
-  dim3 grid(P.tiles_x, P.tiles_y, P.B);
+  dim3 grid(P.ftiles_x, P.ftiles_y, P.B);
   {
     ScopedKernelTimer tm(1, st);
-    float* co = save ? sv.coef : nullptr;
-    auto run = [&](auto kern) { kern<<<grid, kThreads, 0, st>>>(P, ab, sel, Wk.loss_part, Wk.g_part, need_g, co, Wk.iw); };
-    if (P.N == 1) { if (pk) run(k_photo_fwd<1, true>); else run(k_photo_fwd<1, false>); }
-    else { if (pk) run(k_photo_fwd<2, true>); else run(k_photo_fwd<2, false>); }
+    float4* co = save ? reinterpret_cast<float4*>(sv.coef) : nullptr;
+    // opting in to > 48 KB of dynamic shared memory is a per-function, per-device attribute: cheap and idempotent
+    auto run = [&](auto kern, size_t smem) {
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      kern<<<grid, kFwdThreads, smem, st>>>(P, ab, sel, Wk.loss_part, Wk.g_part, need_g, co, Wk.iw);
+    };
+    if (P.N == 1) { if (pk) run(k_photo_fwd<1, true>, photo_fwd_smem<1>()); else run(k_photo_fwd<1, false>, photo_fwd_smem<1>()); }
+    else { if (pk) run(k_photo_fwd<2, true>, photo_fwd_smem<2>()); else run(k_photo_fwd<2, false>, photo_fwd_smem<2>()); }
   }
   {
     auto run = [&](auto kern, bool sv_on) {
@@ -769,7 +575,7 @@ cudaError_t launch_forward(const KP& P, const FwdBuffers& Wk, float* loss, float
 
 cudaError_t launch_consistency(const KP& P, double* stat_part, int stat_chunks, double* pe_part, float* ab, float* out,
                                cudaStream_t st) {
-  k_warp_stats<1, false, false><<<dim3(stat_chunks, P.B), kThreads, 0, st>>>(P, stat_part, nullptr, nullptr);
+  k_warp_stats<1, false, false><<<dim3(stat_chunks, P.B), kThreads, 0, st>>>(P, stat_part, nullptr, nullptr, nullptr);
   k_lcc_solve<<<P.B, 32, 0, st>>>(P, stat_part, stat_chunks, ab, nullptr);
   k_consistency_pe<<<dim3(P.tiles_x, P.tiles_y, P.B), kThreads, 0, st>>>(P, ab, pe_part);
   k_consistency_final<<<P.B, kThreads, 0, st>>>(P, pe_part, ab, out);

@@ -12,6 +12,11 @@ constexpr int kMaxN = 2;
 constexpr int kThreads = 256;
 constexpr int kTileW = 32;       // one warp = one tile row: coalesced 128 B rows
 constexpr int kTileH = 8;
+// forward tile kernel (k_photo_fwd): every warp walks down a strip of windows, one window column per lane
+constexpr int kFwdWarps = 4;     // warps per CTA
+constexpr int kFwdRows = 4;      // window rows per warp
+constexpr int kFwdThreads = kFwdWarps * 32;
+constexpr int kFwdTileH = kFwdWarps * kFwdRows;   // 16
 constexpr int kStatPPT = 8;      // pixels per thread in the LCC statistics pass
 constexpr int kStatVals = 6;     // per (frame, chunk): n, Sx, Sy, Sxx, Sxy, sum of geometric-consistency diffs
 constexpr int kSmoothMaxChunks = 64;
@@ -20,9 +25,11 @@ constexpr int kSmoothPixPerBlock = 1024;
 // saved[] layout: doubles  [B*N*S][kSavedPerFrame]  n, mean_x, mean_y, 1/(n (var+eps)), a, b, G_a, G_b
 //                 doubles  [B*S][kSavedPerScale]    mean inverse depth, sum_p s_p d_p
 //                 floats   s-field of every scale   dL_smooth/dd*_p for grad_loss = 1, [B,h_k,w_k]
-//                 float4   [B,S,H,W,3]              SSIM adjoint coefficients (ca, cb, cg, -) per channel of the
-//                                                   winning re-projection candidate (undefined where identity won);
+//                 float4   [B,S,3,H,W]              SSIM adjoint coefficients (ca, cb, cg, n) per channel of the
+//                                                   winning re-projection candidate n (all zero where identity won);
 //                                                   16-byte texels so the backward stages them with 16 B cp.async
+//                 float4   [B,N,S,H,W]              projection of every pixel (u', v', 1/(Z'+eps), D^ with the valid
+//                                                   bit in its mantissa LSB): the backward does not re-project
 constexpr int kSavedPerFrame = 8;
 constexpr int kSavedPerScale = 2;
 
@@ -45,7 +52,8 @@ struct KP {
   long long frame_el;                // elements per frame in the storage format: 3*HW floats, or HW 8-byte texels
   long long depth_bs[kMaxS];
   int K_bs, T_bs, T_ns;
-  int tiles_x, tiles_y;
+  int tiles_x, tiles_y;               // 32 x 8 tiles of the backward kernel
+  int ftiles_x, ftiles_y;             // 32 x 16 tiles of the forward kernel
 };
 
 __device__ __forceinline__ Cam load_cam(const KP& P, int b) {
@@ -190,6 +198,7 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool pr
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_but_one() { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
 
 // bilinear sample of one extra plane (the source depth map) with the taps of a warped pixel
 __device__ __forceinline__ float sample_plane(const float* __restrict__ plane, const Taps& t, int W, float (&d)[4]) {
@@ -265,7 +274,7 @@ struct FwdBuffers {
   double* smooth_part;   // [B*S][kSmoothMaxChunks][3]   sum_x, sum_y, sum s*d
   double* loss_part;     // [B*tiles]
   double* g_part;        // [B*tiles][N*kMaxS*2]
-  float* iw;             // [B,N,S,3,H,W] raw warped frames (k_warp_stats -> k_photo_fwd)
+  float4* iw;            // [B,N,S,H,W] raw warped frames as (x0, x1, x2, -) texels (k_warp_stats -> k_photo_fwd)
 };
 struct BwdBuffers {
   float* dDhat[kMaxS];   // k >= 1: [B,H,W] full-resolution depth adjoint before the up-sample adjoint
@@ -275,7 +284,8 @@ struct SavedView {       // the caller-owned `saved` buffer, carved
   double* frame;         // [B*N*S][kSavedPerFrame]
   double* scale;         // [B*S][kSavedPerScale]
   float* s_field[kMaxS]; // [B,h_k,w_k]
-  float* coef;           // [B,S,H,W,3] float4: unit-weight SSIM adjoint coefficients of the winning re-projection
+  float* coef;           // [B,S,3,H,W] float4: unit-weight SSIM adjoint coefficients of the winning re-projection
+  float4* geo;           // [B,N,S,H,W] float4: (u', v', iz, D^|valid) of every warped pixel
 };
 
 // one-shot event bracket around one kernel launch (colvo_debug_time_kernel)

@@ -434,6 +434,31 @@ def candidate_gap(depth, pose, K, tgt, srcs, *, alpha=ALPHA, lcc=True):
         return torch.stack(gaps, dim=1)
 
 
+def l1_kink_count(depth, pose, K, tgt, srcs, sel, ab, *, tol: float = 1e-6) -> int:
+    """Number of samples (b, k, pixel, channel) of the WINNING re-projection candidate whose
+    calibrated residual `a*I_w + b - I_t` lies within `tol` of the kink of |.|.
+
+    torch's `abs` has sub-gradient sign(0) = 0 there; a second fp32 evaluation of the same
+    residual (the CUDA kernel's, with fused multiply-adds) can land on the other side of 0 or
+    exactly on it, which changes dL/dI_w of that one sample by up to (1 - alpha)/3 * a / (S B HW)
+    -- the L1 analogue of the arg-min near-tie of SURVEY.md section 7.4 H2.  Parity tests allow that
+    many isolated outliers (bounded in size) and are strict when the count is 0.
+    `sel` / `ab` are the decisions the gradients were computed with."""
+    B, N, S, H, W = _validate(depth, pose, K, tgt, srcs)
+    count = 0
+    with torch.no_grad():
+        for k in range(S):
+            Dhat = upsample_depth(depth[k], H, W)
+            for n in range(N):
+                u, v, _, _ = reproject(Dhat, K, pose[:, n])
+                Iw = bilinear_sample(srcs[:, n], u, v)
+                a = ab[:, n, k, 0].to(Iw.dtype).reshape(B, 1, 1, 1)
+                b = ab[:, n, k, 1].to(Iw.dtype).reshape(B, 1, 1, 1)
+                near = ((a * Iw + b - tgt).abs() < tol) & (sel[:, k].to(torch.long) == N + n).unsqueeze(1)
+                count += int(near.sum().item())
+    return count
+
+
 # --------------------------------------------------------------------------------------
 # SURVEY.md section 8(f)-1 / BASELINE config 5: inference-time warp + LCC consistency.
 # --------------------------------------------------------------------------------------

@@ -52,10 +52,10 @@ def test_workspace_and_saved_sizes():
     assert lib.colvo_saved_doubles(ctypes.byref(d), ctypes.byref(m)) == 0
     assert lib.colvo_step_host_arena_bytes(ctypes.byref(d), ctypes.byref(a)) == 0
     # doubles: 8 per warped frame + 2 per (b, k); then fp32 (2 per double): the smoothness adjoint fields
-    # [B,h_k,w_k] and the SSIM adjoint coefficients [B,S,H,W,3] as float4 texels
-    nf = 12 * (256 * 320 + 128 * 160 + 64 * 80 + 32 * 40) + 12 * 4 * 12 * 256 * 320
+    # [B,h_k,w_k], the SSIM adjoint coefficients [B,S,3,H,W] and the projections [B,N,S,H,W] as float4 texels
+    nf = 12 * (256 * 320 + 128 * 160 + 64 * 80 + 32 * 40) + 12 * 4 * 12 * 256 * 320 + 12 * 2 * 4 * 4 * 256 * 320
     assert m.value == 12 * 2 * 4 * 8 + 12 * 4 * 2 + (nf + 1) // 2
-    iw = 4 * 12 * 2 * 4 * 3 * 256 * 320                      # cached raw warped frames (stats -> tile kernel)
+    iw = 4 * 12 * 2 * 4 * 4 * 256 * 320                      # cached raw warped frames as 16-byte texels (stats -> tile kernel)
     assert iw < n.value < iw + (32 << 20)
     assert a.value > n.value + 4 * 12 * (3 + 6 + 6) * 256 * 320
     assert lib.colvo_workspace_bytes(ctypes.byref(d), None) == -3

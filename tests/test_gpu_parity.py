@@ -19,6 +19,16 @@ def relinf(a, b):
     return (a.cpu() - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
 
 
+def assert_close_upto_kinks(got, ref, kinks, what, atol=0.0):
+    """max-norm parity at TOL, except for at most 8 elements per L1-kink sample (oracle.l1_kink_count: the
+    sample's own depth texel(s) / four bilinear taps), each bounded by 1e-2 of the max.  Strict when kinks == 0."""
+    err = (got - ref).abs()
+    scale = ref.abs().max().item()
+    bad = err > TOL * scale + atol
+    assert int(bad.sum()) <= 8 * kinks, f"{what}: {int(bad.sum())} elements beyond {TOL} (rel {relinf(got, ref)}), {kinks} L1 kinks"
+    assert err.max().item() <= 1e-2 * scale + atol, f"{what}: outlier {relinf(got, ref)}"
+
+
 def run_cuda(d, **kw):
     depth = [x.to(DEV).requires_grad_() for x in d["depth"]]
     pose = d["pose"].to(DEV).requires_grad_()
@@ -50,12 +60,12 @@ def check_against_oracle(d, depth_atol=0.0, **kw):
     osr = d["srcs"].clone().requires_grad_()
     l1 = O.photometric_loss(od, op, d["K"], d["tgt"], osr, sel_override=sel, ab_override=ab, **kw)
     l1.backward()
+    kinks = O.l1_kink_count(d["depth"], d["pose"], d["K"], d["tgt"], d["srcs"], sel, ab) if kw.get("alpha", 0.85) < 1 else 0
     for k in range(S):
-        err = (gd[k] - od[k].grad).abs().max().item()
-        assert err < TOL * od[k].grad.abs().max().item() + depth_atol, f"grad_depth[{k}] {relinf(gd[k], od[k].grad)}"
+        assert_close_upto_kinks(gd[k], od[k].grad, kinks, f"grad_depth[{k}]", depth_atol)
     assert relinf(gT[:, :, :3], op.grad[:, :, :3]) < TOL, f"grad_pose {relinf(gT, op.grad)}"
     assert gT[:, :, 3].abs().max().item() == 0
-    assert relinf(gs, osr.grad) < TOL, f"grad_srcs {relinf(gs, osr.grad)}"
+    assert_close_upto_kinks(gs, osr.grad, kinks, "grad_srcs")
 
 
 @pytest.mark.parametrize("B,H,W,N,S", [
