@@ -66,27 +66,24 @@ void fill_params(KP& P, const ColvoDesc* d) {
   P.tiles_y = div_up(d->H, kTileH);
   P.ftiles_x = div_up(d->W, 32);
   P.ftiles_y = div_up(d->H, kFwdTileH);
-  for (int k = 0; k < d->S; ++k) {
-    int c = div_up(d->h[k] * d->w[k], kSmoothPixPerBlock);
-    P.sm_chunks[k] = c < 1 ? 1 : (c > kSmoothMaxChunks ? kSmoothMaxChunks : c);
-  }
+  P.sm_blocks = div_up(d->W, kSmBW) * div_up(d->H, kSmBH);
 }
+
+size_t smooth_tiles(const ColvoDesc* d) { return (size_t)div_up(d->W, kSmBW) * div_up(d->H, kSmBH) * d->S; }
 
 int stat_chunks(const ColvoDesc* d) { return div_up(d->H * d->W, kThreads * kStatPPT); }
 
 size_t carve_fwd(const ColvoDesc* d, void* ws, FwdBuffers& F) {
   Carver c(ws);
-  const size_t BNS = (size_t)d->B * d->N * d->S, BS = (size_t)d->B * d->S;
+  const size_t BNS = (size_t)d->B * d->N * d->S;
   const size_t tiles = (size_t)div_up(d->W, kTileW) * div_up(d->H, kTileH);
   F.stat_chunks = stat_chunks(d);
   F.stat_part = c.take<double>(BNS * F.stat_chunks * kStatVals);
-  F.disp_part = c.take<double>(BS * kSmoothMaxChunks);
-  F.smooth_part = c.take<double>(BS * kSmoothMaxChunks * 3);
+  F.smooth_part = c.take<double>((size_t)d->B * smooth_tiles(d) * kSmVals);
+  F.smooth_bk = c.take<double>((size_t)d->B * d->S * kSmVals);
   F.loss_part = c.take<double>((size_t)d->B * tiles);
   F.g_part = c.take<double>((size_t)d->B * tiles * d->N * kMaxS * 2);
   F.iw = c.take<float4>(BNS * (size_t)d->H * d->W);
-  F.pyr[0] = nullptr;
-  for (int k = 1; k < kMaxS; ++k) F.pyr[k] = (k < d->S) ? c.take<float>((size_t)d->B * 3 * d->h[k] * d->w[k]) : nullptr;
   return c.off;
 }
 

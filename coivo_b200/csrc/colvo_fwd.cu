@@ -1,12 +1,12 @@
 // Forward kernels of the ColVO photometric-loss path,
 // hand-written for sm_100a.  oracle/photometric.py is the arithmetic contract.
 //
-//   k_prepass       box-averaged target pyramid + partial sums of 1/D per (b,k)      (row 9)
+//   k_smooth        edge-aware smoothness of all scales in one pass over the target: pyramid in
+//                   shared memory, loss partials, adjoint field when saving              (row 9)
 //   k_warp_stats    warp every (b,n,k) frame once, fp64 LCC sums, valid mask          (rows 0-5)
 //   k_lcc_solve     (a, b) per warped frame                                           (row 5)
 //   k_photo_fwd     per 32x8 tile: identity + re-projection candidates, SSIM+L1,
 //                   min-reprojection / auto-mask, loss partials, dL/da, dL/db         (rows 0-8)
-//   k_smooth_fwd    edge-aware smoothness partials (+ its adjoint field when saving)  (row 9)
 //   k_finalize_fwd  deterministic final sums -> loss, G_a, G_b, sum s*d               (row 10)
 #include "colvo_kernels.cuh"
 #include "colvo_photo_fwd.cuh"
@@ -23,72 +23,151 @@ namespace colvo {
 
 static inline int div_up(int a, int b) { return (a + b - 1) / b; }
 
-// block j of a "(b, k, chunk)" launch -> its coordinates; chunks per scale are P.sm_chunks[k]
-__device__ __forceinline__ void decode_chunk(const KP& P, int j, int& b, int& k, int& c) {
-  int tot = 0;
-#pragma unroll
-  for (int i = 0; i < kMaxS; ++i) tot += (i < P.S) ? P.sm_chunks[i] : 0;
-  b = j / tot;
-  int r = j - b * tot;
-  k = 0;
-#pragma unroll
-  for (int i = 0; i < kMaxS - 1; ++i) {
-    if (i < P.S - 1 && k == i && r >= P.sm_chunks[i]) { r -= P.sm_chunks[i]; k = i + 1; }
-  }
-  c = r;
+// ------------------------------------------------------------------------------------------
+// Edge-aware smoothness (row 9) of ALL scales in one pass over the target.  One CTA = one 64x32
+// block of full-resolution pixels of one triplet: it loads that block (+ halo) once, builds the
+// box-averaged pyramid level by level in shared memory (oracle.target_pyramid: the 2^k x 2^k mean
+// is the mean of four means of the level below), and evaluates at every scale its own texels: each
+// visits its four edges -- the right/down ones give the loss, all four give s_p = dL/dd*_p for
+// grad_loss = 1, which the backward only has to rescale.  Level k is kept with a halo of
+// 2^(S-1-k) texels so that level k+1 can be built including its own halo.
+// The mean-disparity normalisation d* = d / (mean d + eps) is a positive per-(b,k) factor, so the
+// sums are formed on d = 1/D and the factor is applied by k_finalize_fwd (|d*_i - d*_j| =
+// |d_i - d_j| / (mean + eps); signs are unchanged).  Depends on the inputs only.
+struct SmoothOut {
+  double* part;            // [B][sm_blocks][S][kSmVals]
+  float* sf[kMaxS];        // adjoint fields [B,h_k,w_k], or null when nothing is saved
+};
+__host__ __device__ constexpr int sm_img_floats() {   // image tiles of all levels at S = kMaxS (halo 8, 4, 2, 1), 3 planes
+  int n = 0;
+  for (int k = 0; k < kMaxS; ++k) n += 3 * ((kSmBW >> k) + 2 * (1 << (kMaxS - 1 - k))) * ((kSmBH >> k) + 2 * (1 << (kMaxS - 1 - k)));
+  return n;
 }
-static inline int total_chunks(const KP& P) {
-  int t = 0;
-  for (int k = 0; k < P.S; ++k) t += P.sm_chunks[k];
-  return t;
+__host__ __device__ constexpr int sm_dep_floats() {   // inverse-depth tiles of all levels, halo 1
+  int n = 0;
+  for (int k = 0; k < kMaxS; ++k) n += ((kSmBW >> k) + 2) * ((kSmBH >> k) + 2);
+  return n;
 }
 
-// ------------------------------------------------------------------------------------------
-// blocks [0, n_pyr): target pyramid, one thread per output texel (block ranges per scale: pyr_off[k]);
-// blocks [n_pyr, ...): sum of 1/D chunks
-struct PyrOff { int off[kMaxS + 1]; };
 template <bool PK>
 __global__ void __launch_bounds__(kThreads)
-    k_prepass(KP P, int n_pyr, PyrOff po, float* p1, float* p2, float* p3, double* __restrict__ disp_part) {
-  __shared__ double sm[kThreads / 32];
-  if ((int)blockIdx.x < n_pyr) {
-    int k = 1;
-    while (k + 1 < P.S && (int)blockIdx.x >= po.off[k + 1]) ++k;
-    float* out = (k == 1) ? p1 : (k == 2 ? p2 : p3);
-    const int hk = P.h[k], wk = P.w[k], f = 1 << k;
-    const int total = P.B * 3 * hk * wk;
-    const int i = (blockIdx.x - po.off[k]) * kThreads + threadIdx.x;
-    if (i >= total) return;
-    const int x = i % wk, r = i / wk;
-    const int y = r % hk, bc = r / hk;
-    const int b = bc / 3, c = bc - 3 * b;
-    const Img<PK> im = img_at<PK>(P, P.tgt, b * P.tgt_bf);
-    const int o = (y * f) * P.W + x * f;
-    float s = 0.f;
-    for (int dy = 0; dy < f; ++dy) {
-      float rs = 0.f;
-      for (int dx = 0; dx < f; ++dx) {
-        if constexpr (PK) {
-          float v[3];
-          im.load3(o + dy * P.W + dx, v);
-          rs += (c == 0) ? v[0] : (c == 1 ? v[1] : v[2]);
-        } else {
-          rs += __ldg(im.p + (c * P.HW + o + dy * P.W + dx));
+    k_smooth(KP P, SmoothOut O) {
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  float* simg = reinterpret_cast<float*>(sm_raw);
+  float* sdep = simg + sm_img_floats();
+  double* red = reinterpret_cast<double*>(sdep + ((sm_dep_floats() + 1) & ~1));
+  const int tid = threadIdx.x, b = blockIdx.z;
+  const int X0 = blockIdx.x * kSmBW, Y0 = blockIdx.y * kSmBH;
+  const Img<PK> im = img_at<PK>(P, P.tgt, b * P.tgt_bf);
+
+  int ioff[kMaxS], doff[kMaxS];          // smem offsets of the level tiles
+  {
+    int io = 0, dof = 0;
+#pragma unroll
+    for (int k = 0; k < kMaxS; ++k) {
+      ioff[k] = io;
+      doff[k] = dof;
+      const int hal = (k < P.S) ? (1 << (P.S - 1 - k)) : 0;
+      io += 3 * ((kSmBW >> k) + 2 * hal) * ((kSmBH >> k) + 2 * hal);
+      dof += ((kSmBW >> k) + 2) * ((kSmBH >> k) + 2);
+    }
+  }
+  // ---- level 0: the full-resolution block + halo, and the inverse-depth tiles of every scale ----
+  {
+    const int hal = 1 << (P.S - 1), dw = kSmBW + 2 * hal, dh = kSmBH + 2 * hal, dn = dw * dh;
+    for (int idx = tid; idx < dn; idx += kThreads) {
+      const int r = idx / dw, c = idx - r * dw;
+      const int gy = Y0 - hal + r, gx = X0 - hal + c;
+      float v[3] = {0.f, 0.f, 0.f};
+      if (gy >= 0 && gy < P.H && gx >= 0 && gx < P.W) im.load3(gy * P.W + gx, v);
+      simg[idx] = v[0];
+      simg[dn + idx] = v[1];
+      simg[2 * dn + idx] = v[2];
+    }
+#pragma unroll
+    for (int k = 0; k < kMaxS; ++k) {
+      if (k < P.S) {
+        const int hk = P.h[k], wk = P.w[k], dwk = (kSmBW >> k) + 2, dnk = dwk * ((kSmBH >> k) + 2);
+        const float* D = P.depth[k] + (long long)b * P.depth_bs[k];
+        for (int idx = tid; idx < dnk; idx += kThreads) {
+          const int r = idx / dwk, c = idx - r * dwk;
+          const int gy = (Y0 >> k) - 1 + r, gx = (X0 >> k) - 1 + c;
+          sdep[doff[k] + idx] = (gy >= 0 && gy < hk && gx >= 0 && gx < wk) ? f_rcp(__ldg(D + gy * wk + gx)) : 0.f;
         }
       }
-      s += rs;
     }
-    out[i] = s * (1.0f / (float)(f * f));
-    return;
   }
-  int b, k, c;
-  decode_chunk(P, blockIdx.x - n_pyr, b, k, c);
-  const int n = P.h[k] * P.w[k], C = P.sm_chunks[k];
-  const float* D = P.depth[k] + (long long)b * P.depth_bs[k];
-  double acc = 0.0;
-  for (int i = c * kThreads + threadIdx.x; i < n; i += C * kThreads) acc += (double)f_rcp(__ldg(D + i));
-  double v[1] = {acc};
-  block_reduce_store<1, double>(v, sm, disp_part + ((long long)(b * P.S + k)) * kSmoothMaxChunks + c);
+  __syncthreads();
+  // ---- levels 1 .. S-1: mean of the four texels below ----
+#pragma unroll
+  for (int k = 1; k < kMaxS; ++k) {
+    if (k < P.S) {
+      const int hal = 1 << (P.S - 1 - k), dw = (kSmBW >> k) + 2 * hal, dh = (kSmBH >> k) + 2 * hal, dn = dw * dh;
+      const int pdw = (kSmBW >> (k - 1)) + 4 * hal, pdn = pdw * ((kSmBH >> (k - 1)) + 4 * hal);
+      const float* src = simg + ioff[k - 1];
+      float* dst = simg + ioff[k];
+      for (int idx = tid; idx < dn; idx += kThreads) {
+        const int r = idx / dw, c = idx - r * dw;
+        const int o = (2 * r) * pdw + 2 * c;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+          const float* q = src + ch * pdn + o;
+          dst[ch * dn + idx] = ((q[0] + q[1]) + (q[pdw] + q[pdw + 1])) * 0.25f;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // ---- smoothness of the own texels of every scale ----
+  const int blk = (b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+#pragma unroll 1
+  for (int k = 0; k < P.S; ++k) {
+    const int hk = P.h[k], wk = P.w[k];
+    const int hal = 1 << (P.S - 1 - k), tw = kSmBW >> k, th = kSmBH >> k;
+    const int dw = tw + 2 * hal, dn = dw * (th + 2 * hal), ddw = tw + 2;
+    const float* I = simg + ioff[k];
+    const float* Dr = sdep + doff[k];
+    float* sf = O.sf[k] ? O.sf[k] + (long long)b * hk * wk : nullptr;
+    const double lam = (double)P.smooth_weight / (double)(1 << k) / (double)P.S;
+    const double nx = (double)P.B * hk * (wk - 1), ny = (double)P.B * (hk - 1) * wk;
+    const float cx = nx > 0 ? (float)(lam / nx) : 0.f, cy = ny > 0 ? (float)(lam / ny) : 0.f;
+    float acc[kSmVals] = {0.f, 0.f, 0.f, 0.f};      // at most 8 texels per thread and scale: fp32, then fp64 across threads
+    for (int i = tid; i < tw * th; i += kThreads) {
+      const int ly = i / tw, lx = i - ly * tw;
+      const int gy = (Y0 >> k) + ly, gx = (X0 >> k) + lx;
+      if (gy < hk && gx < wk) {
+        const int o = (ly + hal) * dw + lx + hal, od = (ly + 1) * ddw + lx + 1;
+        const float i0 = I[o], i1 = I[dn + o], i2 = I[2 * dn + o], dr = Dr[od];
+        auto edge = [&](int oj, int odj) -> float2 {   // (d_i - d_j, exp(-mean_c |I_i - I_j|))
+          const float e = (fabsf(i0 - I[oj]) + fabsf(i1 - I[dn + oj]) + fabsf(i2 - I[2 * dn + oj])) * (1.0f / 3.0f);
+          return make_float2(dr - Dr[odj], __expf(-e));   // e in [0, 1]: MUFU.EX2 path, rel. error ~1e-6
+        };
+        float s = 0.f;
+        if (gx + 1 < wk) {
+          const float2 e = edge(o + 1, od + 1);
+          acc[0] += fabsf(e.x) * e.y;
+          s += sgn(e.x) * e.y * cx;
+        }
+        if (gy + 1 < hk) {
+          const float2 e = edge(o + dw, od + ddw);
+          acc[1] += fabsf(e.x) * e.y;
+          s += sgn(e.x) * e.y * cy;
+        }
+        if (sf) {
+          if (gx > 0) { const float2 e = edge(o - 1, od - 1); s += sgn(e.x) * e.y * cx; }
+          if (gy > 0) { const float2 e = edge(o - dw, od - ddw); s += sgn(e.x) * e.y * cy; }
+          sf[gy * wk + gx] = s;
+          acc[2] = fmaf(s, dr, acc[2]);
+        }
+        acc[3] += dr;
+      }
+    }
+    double accd[kSmVals];
+#pragma unroll
+    for (int j = 0; j < kSmVals; ++j) accd[j] = (double)acc[j];
+    block_reduce_store<kSmVals, double>(accd, red, O.part + ((long long)blk * P.S + k) * kSmVals);
+    __syncthreads();          // red is reused by the next scale
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -179,8 +258,25 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_STATS)
 
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32)
-    k_lcc_solve(KP P, const double* __restrict__ part, int chunks, float* __restrict__ ab, double* __restrict__ saved) {
+    k_lcc_solve(KP P, const double* __restrict__ part, int chunks, float* __restrict__ ab, double* __restrict__ saved,
+                const double* __restrict__ smooth_part, double* __restrict__ smooth_bk) {
   const int bnk = blockIdx.x, lane = threadIdx.x;
+  if (bnk >= P.B * P.N * P.S) {        // extra blocks: the smoothness partials of (b, k), summed in a fixed order
+    const int bk = bnk - P.B * P.N * P.S, b = bk / P.S, k = bk - b * P.S;
+    const double* sp = smooth_part + ((long long)b * P.sm_blocks * P.S + k) * kSmVals;
+    double v[kSmVals] = {0.0, 0.0, 0.0, 0.0};
+    for (int t = lane; t < P.sm_blocks; t += 32) {
+#pragma unroll
+      for (int j = 0; j < kSmVals; ++j) v[j] += sp[(long long)t * P.S * kSmVals + j];
+    }
+#pragma unroll
+    for (int j = 0; j < kSmVals; ++j) v[j] = warp_sum(v[j]);
+    if (lane == 0) {
+#pragma unroll
+      for (int j = 0; j < kSmVals; ++j) smooth_bk[bk * kSmVals + j] = v[j];
+    }
+    return;
+  }
   double s[5] = {0, 0, 0, 0, 0};
   if (P.flags & 1u) {
     for (int c = lane; c < chunks; c += 32) {
@@ -282,87 +378,11 @@ __device__ __forceinline__ void ywin_init(YWin& y, const float* ys, int own) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Smoothness (row 9).  Each pixel visits its four edges: the right/down ones give the loss, all
-// four give s_p = dL/dd*_p (for grad_loss = 1), which the backward only has to rescale.
-template <bool SAVE, bool PK>
-__global__ void __launch_bounds__(kThreads)
-    k_smooth_fwd(KP P, const double* __restrict__ disp_part, const float* p1, const float* p2, const float* p3,
-                 double* __restrict__ smooth_part, double* __restrict__ saved_scale, float* s0, float* s1, float* s2,
-                 float* s3) {
-  __shared__ double sm[(kThreads / 32) * 3];
-  __shared__ double mean_s;
-  int b, k, c;
-  decode_chunk(P, blockIdx.x, b, k, c);
-  const int bk = b * P.S + k;
-  const int hk = P.h[k], wk = P.w[k], n = hk * wk, C = P.sm_chunks[k];
-  if (threadIdx.x < 32) {
-    double s = 0.0;
-    for (int i = threadIdx.x; i < C; i += 32) s += disp_part[(long long)bk * kSmoothMaxChunks + i];
-    s = warp_sum(s);
-    if (threadIdx.x == 0) {
-      mean_s = s / (double)n;
-      if (SAVE && c == 0) saved_scale[bk * kSavedPerScale + 0] = mean_s;
-    }
-  }
-  __syncthreads();
-  const float inv = (float)(1.0 / (mean_s + (double)P.eps_disp));
-  const float* D = P.depth[k] + (long long)b * P.depth_bs[k];
-  // image of this scale: the target itself (either storage format) at k = 0, the fp32 pyramid above
-  const Img<PK> I0 = img_at<PK>(P, P.tgt, b * P.tgt_bf);
-  Img<false> Ik;
-  Ik.p = (k == 0) ? nullptr : ((k == 1) ? p1 : (k == 2 ? p2 : p3)) + (long long)b * 3 * n;
-  Ik.HW = n;
-  float* sf = nullptr;
-  if (SAVE) sf = ((k == 0) ? s0 : (k == 1 ? s1 : (k == 2 ? s2 : s3))) + (long long)b * n;
-  const double lam = (double)P.smooth_weight / (double)(1 << k) / (double)P.S;
-  const double nx = (double)P.B * hk * (wk - 1), ny = (double)P.B * (hk - 1) * wk;
-  const float cx = nx > 0 ? (float)(lam / nx) : 0.f, cy = ny > 0 ? (float)(lam / ny) : 0.f;
-  double acc[3] = {0.0, 0.0, 0.0};
-  auto run = [&](const auto& img) {
-    for (int i = c * kThreads + threadIdx.x; i < n; i += C * kThreads) {
-      const int y = i / wk, x = i - y * wk;
-      const float dr = f_rcp(__ldg(D + i));
-      const float d = dr * inv;
-      float iv[3];
-      img.load3(i, iv);
-      const float i0 = iv[0], i1 = iv[1], i2 = iv[2];
-      float s = 0.f;
-      auto edge = [&](int j) -> float2 {   // (d_i - d_j, exp(-mean_c |I_i - I_j|))
-        float dn = f_rcp(__ldg(D + j)) * inv;
-        float jv[3];
-        img.load3(j, jv);
-        float e = (fabsf(i0 - jv[0]) + fabsf(i1 - jv[1]) + fabsf(i2 - jv[2])) * (1.0f / 3.0f);
-        return make_float2(d - dn, __expf(-e));   // e in [0, 1]: MUFU.EX2 path, rel. error ~1e-6
-      };
-      if (x + 1 < wk) {
-        float2 t = edge(i + 1);
-        acc[0] += (double)(fabsf(t.x) * t.y);
-        if (SAVE) s += sgn(t.x) * t.y * cx;
-      }
-      if (y + 1 < hk) {
-        float2 t = edge(i + wk);
-        acc[1] += (double)(fabsf(t.x) * t.y);
-        if (SAVE) s += sgn(t.x) * t.y * cy;
-      }
-      if (SAVE) {
-        if (x > 0) { float2 t = edge(i - 1); s += sgn(t.x) * t.y * cx; }
-        if (y > 0) { float2 t = edge(i - wk); s += sgn(t.x) * t.y * cy; }
-        sf[i] = s;
-        acc[2] += (double)(s * dr);
-      }
-    }
-  };
-  if (k == 0) run(I0);
-  else run(Ik);
-  block_reduce_store<3, double>(acc, sm, smooth_part + ((long long)bk * kSmoothMaxChunks + c) * 3);
-}
-
-// ------------------------------------------------------------------------------------------
 // block 0: the scalar loss.  blocks [1, 1+BNS): G_a, G_b of warped frame bnk (dL/da, dL/db).
-// blocks [1+BNS, 1+BNS+B*S): sum_p s_p d_p of (b, k) for the smoothness adjoint.
+// blocks [1+BNS, 1+BNS+B*S): mean inverse depth and sum_p s_p d_p of (b, k) for the smoothness adjoint.
 __global__ void __launch_bounds__(kThreads)
     k_finalize_fwd(KP P, const double* __restrict__ loss_part, const double* __restrict__ g_part,
-                   const double* __restrict__ smooth_part, const double* __restrict__ stat_part, int stat_chunks,
+                   const double* __restrict__ smooth_bk, const double* __restrict__ stat_part, int stat_chunks,
                    float* __restrict__ loss, double* __restrict__ saved_frame, double* __restrict__ saved_scale,
                    int need_g) {
   __shared__ double sm[(kThreads / 32) * 2];
@@ -390,10 +410,12 @@ __global__ void __launch_bounds__(kThreads)
       const double wg = (double)P.geo_weight / ((double)P.B * (double)P.N * (double)P.HW);
       for (int i = threadIdx.x; i < BNS * stat_chunks; i += kThreads) acc[1] += stat_part[(long long)i * kStatVals + 5] * wg;
     }
-    for (int i = threadIdx.x; i < P.B * P.S * kSmoothMaxChunks; i += kThreads) {
-      const int bk = i / kSmoothMaxChunks, c = i - bk * kSmoothMaxChunks, k = bk % P.S;
-      if (c < P.sm_chunks[k])
-        acc[1] += smooth_part[(long long)i * 3 + 0] * wk_s[k][0] + smooth_part[(long long)i * 3 + 1] * wk_s[k][1];
+    // smoothness: per-(b, k) sums (k_lcc_solve's extra blocks), normalised by 1 / (mean d + eps) (see k_smooth)
+    for (int bk = threadIdx.x; bk < P.B * P.S; bk += kThreads) {
+      const int k = bk % P.S;
+      const double* v = smooth_bk + bk * kSmVals;
+      const double mean = v[3] / ((double)P.h[k] * (double)P.w[k]);
+      acc[1] += (v[0] * wk_s[k][0] + v[1] * wk_s[k][1]) / (mean + (double)P.eps_disp);
     }
     for (int j = 0; j < 2; ++j) {
       double s = warp_sum(acc[j]);
@@ -432,13 +454,11 @@ __global__ void __launch_bounds__(kThreads)
     }
     return;
   }
-  // sum_p s_p d_p
+  // mean inverse depth and sum_p s_p d_p of (b, k), for the smoothness adjoint
   const int bk = blockIdx.x - 1 - BNS, k = bk % P.S;
-  if (threadIdx.x < 32) {
-    double s = 0.0;
-    for (int c = lane; c < P.sm_chunks[k]; c += 32) s += smooth_part[((long long)bk * kSmoothMaxChunks + c) * 3 + 2];
-    s = warp_sum(s);
-    if (lane == 0) saved_scale[bk * kSavedPerScale + 1] = s;
+  if (threadIdx.x == 0) {
+    saved_scale[bk * kSavedPerScale + 0] = smooth_bk[bk * kSmVals + 3] / ((double)P.h[k] * (double)P.w[k]);
+    saved_scale[bk * kSavedPerScale + 1] = smooth_bk[bk * kSmVals + 2];
   }
 }
 
@@ -520,18 +540,19 @@ cudaError_t launch_forward(const KP& P, const FwdBuffers& Wk, float* loss, float
   const bool save = (P.flags & 4u) != 0;
   const int need_g = (save && lcc && !(P.flags & 2u)) ? 1 : 0;
   const int BNS = P.B * P.N * P.S;
-  const int chunks = P.B * total_chunks(P);
-  PyrOff po;
-  int n_pyr = 0;
-  po.off[0] = 0;
-  for (int k = 1; k <= kMaxS; ++k) {
-    if (k < kMaxS) po.off[k] = n_pyr;
-    else po.off[kMaxS] = n_pyr;
-    if (k < P.S) n_pyr += div_up(P.B * 3 * P.h[k] * P.w[k], kThreads);
-  }
   const bool pk = (P.flags & 16u) != 0;
-  if (pk) k_prepass<true><<<n_pyr + chunks, kThreads, 0, st>>>(P, n_pyr, po, Wk.pyr[1], Wk.pyr[2], Wk.pyr[3], Wk.disp_part);
-  else k_prepass<false><<<n_pyr + chunks, kThreads, 0, st>>>(P, n_pyr, po, Wk.pyr[1], Wk.pyr[2], Wk.pyr[3], Wk.disp_part);
+  {
+    SmoothOut smo;
+    smo.part = Wk.smooth_part;
+    for (int k = 0; k < kMaxS; ++k) smo.sf[k] = save ? sv.s_field[k] : nullptr;
+    const size_t smem = sizeof(float) * (sm_img_floats() + ((sm_dep_floats() + 1) & ~1)) + sizeof(double) * (kThreads / 32) * kSmVals;
+    dim3 g(div_up(P.W, kSmBW), div_up(P.H, kSmBH), P.B);
+    auto run = [&](auto kern) {
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      kern<<<g, kThreads, smem, st>>>(P, smo);
+    };
+    if (pk) run(k_smooth<true>); else run(k_smooth<false>);
+  }
   {
     ScopedKernelTimer tm(3, st);
     dim3 g(Wk.stat_chunks, P.B * P.S);
@@ -545,7 +566,8 @@ cudaError_t launch_forward(const KP& P, const FwdBuffers& Wk, float* loss, float
       else { if (pk) run(k_warp_stats<2, false, true>); else run(k_warp_stats<2, false, false>); }
     }
   }
-  k_lcc_solve<<<BNS, 32, 0, st>>>(P, Wk.stat_part, Wk.stat_chunks, ab, save ? sv.frame : nullptr);
+  k_lcc_solve<<<BNS + P.B * P.S, 32, 0, st>>>(P, Wk.stat_part, Wk.stat_chunks, ab, save ? sv.frame : nullptr, Wk.smooth_part,
+                                              Wk.smooth_bk);
   dim3 grid(P.ftiles_x, P.ftiles_y, P.B);
   {
     ScopedKernelTimer tm(1, st);
@@ -558,17 +580,8 @@ cudaError_t launch_forward(const KP& P, const FwdBuffers& Wk, float* loss, float
     if (P.N == 1) { if (pk) run(k_photo_fwd<1, true>, photo_fwd_smem<1>()); else run(k_photo_fwd<1, false>, photo_fwd_smem<1>()); }
     else { if (pk) run(k_photo_fwd<2, true>, photo_fwd_smem<2>()); else run(k_photo_fwd<2, false>, photo_fwd_smem<2>()); }
   }
-  {
-    auto run = [&](auto kern, bool sv_on) {
-      kern<<<chunks, kThreads, 0, st>>>(P, Wk.disp_part, Wk.pyr[1], Wk.pyr[2], Wk.pyr[3], Wk.smooth_part, sv_on ? sv.scale : nullptr,
-                                        sv_on ? sv.s_field[0] : nullptr, sv_on ? sv.s_field[1] : nullptr,
-                                        sv_on ? sv.s_field[2] : nullptr, sv_on ? sv.s_field[3] : nullptr);
-    };
-    if (save) { if (pk) run(k_smooth_fwd<true, true>, true); else run(k_smooth_fwd<true, false>, true); }
-    else { if (pk) run(k_smooth_fwd<false, true>, false); else run(k_smooth_fwd<false, false>, false); }
-  }
   const int nfin = 1 + (save ? BNS + P.B * P.S : 0);
-  k_finalize_fwd<<<nfin, kThreads, 0, st>>>(P, Wk.loss_part, Wk.g_part, Wk.smooth_part, Wk.stat_part, Wk.stat_chunks,
+  k_finalize_fwd<<<nfin, kThreads, 0, st>>>(P, Wk.loss_part, Wk.g_part, Wk.smooth_bk, Wk.stat_part, Wk.stat_chunks,
                                             loss, sv.frame, sv.scale, need_g);
   return cudaGetLastError();
 }
@@ -576,7 +589,7 @@ cudaError_t launch_forward(const KP& P, const FwdBuffers& Wk, float* loss, float
 cudaError_t launch_consistency(const KP& P, double* stat_part, int stat_chunks, double* pe_part, float* ab, float* out,
                                cudaStream_t st) {
   k_warp_stats<1, false, false><<<dim3(stat_chunks, P.B), kThreads, 0, st>>>(P, stat_part, nullptr, nullptr, nullptr);
-  k_lcc_solve<<<P.B, 32, 0, st>>>(P, stat_part, stat_chunks, ab, nullptr);
+  k_lcc_solve<<<P.B, 32, 0, st>>>(P, stat_part, stat_chunks, ab, nullptr, nullptr, nullptr);
   k_consistency_pe<<<dim3(P.tiles_x, P.tiles_y, P.B), kThreads, 0, st>>>(P, ab, pe_part);
   k_consistency_final<<<P.B, kThreads, 0, st>>>(P, pe_part, ab, out);
   return cudaGetLastError();

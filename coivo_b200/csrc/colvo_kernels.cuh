@@ -19,8 +19,8 @@ constexpr int kFwdThreads = kFwdWarps * 32;
 constexpr int kFwdTileH = kFwdWarps * kFwdRows;   // 16
 constexpr int kStatPPT = 8;      // pixels per thread in the LCC statistics pass
 constexpr int kStatVals = 6;     // per (frame, chunk): n, Sx, Sy, Sxx, Sxy, sum of geometric-consistency diffs
-constexpr int kSmoothMaxChunks = 64;
-constexpr int kSmoothPixPerBlock = 1024;
+constexpr int kSmBW = 64, kSmBH = 32; // full-resolution pixels per smoothness block (k_smooth)
+constexpr int kSmVals = 4;            // per block and scale: sum over x edges, sum over y edges, sum s*d, sum d
 
 // saved[] layout: doubles  [B*N*S][kSavedPerFrame]  n, mean_x, mean_y, 1/(n (var+eps)), a, b, G_a, G_b
 //                 doubles  [B*S][kSavedPerScale]    mean inverse depth, sum_p s_p d_p
@@ -37,7 +37,7 @@ struct KP {
   int B, N, S, H, W, HW;
   int h[kMaxS], w[kMaxS];
   float ry[kMaxS], rx[kMaxS];        // h_k / H, w_k / W rounded once to fp32 (oracle._upsample_axis)
-  int sm_chunks[kMaxS];              // smoothness CTAs per (b, k)
+  int sm_blocks;                     // k_smooth CTAs per image
   float alpha, c1, c2, eps_proj, eps_lcc, eps_disp, z_min, smooth_weight;
   unsigned flags;
   const void* tgt;                   // [B,3,H,W] fp32 planar, or [B,H,W,4] bf16 packed (COLVO_F_PACKED_BF16)
@@ -198,7 +198,9 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool pr
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_but_one() { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_but() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void cp_async_wait_but_one() { cp_async_wait_but<1>(); }
 
 // bilinear sample of one extra plane (the source depth map) with the taps of a warped pixel
 __device__ __forceinline__ float sample_plane(const float* __restrict__ plane, const Taps& t, int W, float (&d)[4]) {
@@ -269,9 +271,8 @@ __device__ __forceinline__ void block_sum_slots(const float* slots, double* part
 struct FwdBuffers {
   double* stat_part;     // [B*N*S][stat_chunks][kStatVals]
   int stat_chunks;
-  float* pyr[kMaxS];     // target pyramid, k >= 1: [B,3,h_k,w_k]
-  double* disp_part;     // [B*S][kSmoothMaxChunks]
-  double* smooth_part;   // [B*S][kSmoothMaxChunks][3]   sum_x, sum_y, sum s*d
+  double* smooth_part;   // [B][sm_blocks][S][kSmVals] per k_smooth CTA and scale: sum_x, sum_y, sum s*d, sum d (un-normalised)
+  double* smooth_bk;     // [B*S][kSmVals]            the same, summed per (b, k) by the extra blocks of k_lcc_solve
   double* loss_part;     // [B*tiles]
   double* g_part;        // [B*tiles][N*kMaxS*2]
   float4* iw;            // [B,N,S,H,W] raw warped frames as (x0, x1, x2, -) texels (k_warp_stats -> k_photo_fwd)

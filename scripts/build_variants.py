@@ -5,11 +5,10 @@ from coivo_b200 import _lib
 
 VARIANTS = {
     "base": [],
-    "f4": ["COLVO_MINB_FWD=4"],
-    "f2y": ["COLVO_MINB_FWD=2", "COLVO_Y_REGS=1"],
-    "s3": ["COLVO_MINB_STATS=3"],
-    "s5": ["COLVO_MINB_STATS=5"],
+    "bpf": ["COLVO_BWD_PREFETCH=1"],
+    "bpf2": ["COLVO_BWD_PREFETCH=1", "COLVO_MINB_BWD=2"],
     "b2": ["COLVO_MINB_BWD=2"],
+    "f2": ["COLVO_MINB_FWD=2"],
 }
 out = os.path.join(os.path.dirname(_lib.PKG_DIR), "build", "variants")
 os.makedirs(out, exist_ok=True)
