@@ -94,6 +94,7 @@ size_t carve_bwd(const ColvoDesc* d, void* ws, BwdBuffers& Bw) {
   Bw.dDhat[0] = nullptr;
   for (int k = 1; k < kMaxS; ++k) Bw.dDhat[k] = (k < d->S) ? c.take<float>((size_t)d->B * HW) : nullptr;
   Bw.pose_part = c.take<double>((size_t)d->B * tiles * d->N * 12);
+  Bw.gsrc4 = (d->flags & COLVO_F_NO_SRC_GRAD) ? nullptr : c.take<float4>((size_t)d->B * d->N * HW);
   return c.off;
 }
 

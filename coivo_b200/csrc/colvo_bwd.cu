@@ -12,6 +12,15 @@
 //   k_pose_final     deterministic reduction of the pose-gradient partials
 #include "colvo_kernels.cuh"
 
+#ifndef COLVO_EXP_NOBAR      // timing experiments only (wrong results)
+#define COLVO_EXP_NOBAR 0
+#endif
+#ifndef COLVO_EXP_NOGATHER
+#define COLVO_EXP_NOGATHER 0
+#endif
+#ifndef COLVO_EXP_NORED
+#define COLVO_EXP_NORED 0
+#endif
 #ifndef COLVO_MINB_BWD      // CTAs per SM the register allocator must allow -- tuned on B200, see DESIGN.md
 #define COLVO_MINB_BWD 3
 #endif
@@ -48,7 +57,7 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_BWD)
                 const float* __restrict__ s_field0, const float* __restrict__ coef_in,
                 const float4* __restrict__ geo_in, float* __restrict__ grad_d0,
                 float* __restrict__ dD1, float* __restrict__ dD2, float* __restrict__ dD3,
-                float* __restrict__ grad_srcs, float* __restrict__ grad_src_depth, double* __restrict__ pose_part) {
+                float4* __restrict__ gsrc4, float* __restrict__ grad_src_depth, double* __restrict__ pose_part) {
   // dynamic shared memory, carved by hand
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4 (*coef)[kCN * 3] = reinterpret_cast<float4 (*)[kCN * 3]>(smem_raw);   // [2]: (ca, cb, cg, n) per window
@@ -148,7 +157,9 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_BWD)
     for (int n = 0; n < NS; ++n) gt[n] = __ldg(geo_in + (long long)((b * P.N + n) * P.S + k) * P.HW + qo);
     const int own_sel = __ldg(sel + ((long long)b * P.S + k) * P.HW + qo);
     cp_async_wait_all();
+#if !COLVO_EXP_NOBAR
     __syncthreads();   // scale k landed for every thread (first pass: constants visible), nobody reads the other buffer
+#endif
     if (k + 1 < P.S) stage_coef(k + 1);
     float dD = 0.f;
     // gather once per scale: every window centre has at most one winning source (texel .w = its index), so its
@@ -159,7 +170,7 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_BWD)
     for (int n = 0; n < NS; ++n)
 #pragma unroll
       for (int ch = 0; ch < 3; ++ch) A[n][ch] = Bc[n][ch] = G[n][ch] = 0.f;
-    if (in_img) {
+    if (in_img && !COLVO_EXP_NOGATHER) {
 #pragma unroll
       for (int j = 0; j < 9; ++j) {
         const int o = oc + (j / 3) * kCW + (j % 3);
@@ -218,19 +229,17 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_BWD)
           du = fmaf(h, dux, du);
           dv = fmaf(h, dvy, dv);
         }
-        if (grad_srcs) {
-          // (grad_srcs is planar fp32 [B,N,3,H,W]; it is null for packed sources: quantised images carry no gradient)
+        if (gsrc4 && !COLVO_EXP_NORED) {
+          // scatter into the texel-interleaved gradient buffer: one 16-byte vector RED per tap carries the three
+          // channels (a third of the L2 atomic requests of a planar scatter); null for packed sources, whose
+          // quantised images carry no gradient
           const float w11 = t.wx * t.wy, w01 = t.wx - w11, w10 = t.wy - w11, w00 = 1.f - t.wx - w10;
-          float* gs = grad_srcs + (b * P.src_bf + n * P.src_nf) * (3ll * P.HW);
-          float *g00 = gs + (r0 + t.x0), *g01 = gs + (r0 + t.x1), *g10 = gs + (r1 + t.x0), *g11 = gs + (r1 + t.x1);
-#pragma unroll
-          for (int ch = 0; ch < 3; ++ch) {
-            atomicAdd(g00, w00 * hq[ch]);
-            atomicAdd(g01, w01 * hq[ch]);
-            atomicAdd(g10, w10 * hq[ch]);
-            atomicAdd(g11, w11 * hq[ch]);
-            g00 += P.HW; g01 += P.HW; g10 += P.HW; g11 += P.HW;
-          }
+          float4* gs = gsrc4 + (long long)(b * P.N + n) * P.HW;
+          asm volatile("" : "+l"(gs));      // materialised base: one IMAD.WIDE per address (see Img<false>::load_taps)
+          red_add3(gs + (unsigned)(r0 + t.x0), w00 * hq[0], w00 * hq[1], w00 * hq[2]);
+          red_add3(gs + (unsigned)(r0 + t.x1), w01 * hq[0], w01 * hq[1], w01 * hq[2]);
+          red_add3(gs + (unsigned)(r1 + t.x0), w10 * hq[0], w10 * hq[1], w10 * hq[2]);
+          red_add3(gs + (unsigned)(r1 + t.x1), w11 * hq[0], w11 * hq[1], w11 * hq[2]);
         }
         // geometric consistency (f-2): gradient to Z' directly, to the sampled source depth (scatter) and,
         // through its spatial derivative, to (u', v')
@@ -293,8 +302,28 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_BWD)
 
 // ------------------------------------------------------------------------------------------
 // grad_T[b,n] from the per-tile partials: one CTA per (b,n); warp w reduces entries w, w+8.
+// The blocks beyond B*N unpack the texel-interleaved source gradient into the planar grad_srcs [B,N,3,H,W]
+// (kUnpackPix pixels of one (b,n) frame each; independent of the pose reduction, so it shares the launch).
+constexpr int kUnpackPix = 4 * kThreads;
 __global__ void __launch_bounds__(kThreads)
-    k_pose_final(KP P, const double* __restrict__ pose_part, float* __restrict__ grad_T) {
+    k_pose_final(KP P, const double* __restrict__ pose_part, float* __restrict__ grad_T,
+                 const float4* __restrict__ gsrc4, float* __restrict__ grad_srcs, int unpack_chunks) {
+  if ((int)blockIdx.x >= P.B * P.N) {
+    const int j = blockIdx.x - P.B * P.N, bn = j / unpack_chunks, c = j - bn * unpack_chunks;
+    const float4* src = gsrc4 + (long long)bn * P.HW;
+    float* dst = grad_srcs + (long long)bn * 3 * P.HW;
+#pragma unroll
+    for (int i = 0; i < kUnpackPix / kThreads; ++i) {
+      const int p = c * kUnpackPix + i * kThreads + threadIdx.x;
+      if (p < P.HW) {
+        const float4 g = __ldcs(src + p);
+        dst[p] = g.x;
+        dst[P.HW + p] = g.y;
+        dst[2 * (long long)P.HW + p] = g.z;
+      }
+    }
+    return;
+  }
   const int bn = blockIdx.x, b = bn / P.N, n = bn % P.N;
   const int tiles = P.tiles_x * P.tiles_y, nv = P.N * 12;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -399,7 +428,7 @@ cudaError_t launch_backward(const KP& P, const BwdBuffers& Wk, const float* grad
     if (e != cudaSuccess) return e;
   }
   if (grad_srcs) {
-    e = cudaMemsetAsync(grad_srcs, 0, sizeof(float) * (size_t)P.B * P.N * 3 * P.HW, st);
+    e = cudaMemsetAsync(Wk.gsrc4, 0, sizeof(float4) * (size_t)P.B * P.N * P.HW, st);
     if (e != cudaSuccess) return e;
   }
   dim3 grid(P.tiles_x, P.tiles_y, P.B);
@@ -409,7 +438,8 @@ cudaError_t launch_backward(const KP& P, const BwdBuffers& Wk, const float* grad
     auto launch = [&](auto kern, size_t smem) {
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       kern<<<grid, kThreads, smem, st>>>(P, grad_loss, sel, sv.frame, sv.scale, sv.s_field[0], sv.coef, sv.geo, grad_depth[0],
-                                         Wk.dDhat[1], Wk.dDhat[2], Wk.dDhat[3], grad_srcs, grad_src_depth, Wk.pose_part);
+                                         Wk.dDhat[1], Wk.dDhat[2], Wk.dDhat[3], grad_srcs ? Wk.gsrc4 : nullptr, grad_src_depth,
+                                         Wk.pose_part);
     };
     const bool geo = P.src_depth != nullptr, pk = (P.flags & 16u) != 0;
     if (P.N == 1) {
@@ -420,7 +450,8 @@ cudaError_t launch_backward(const KP& P, const BwdBuffers& Wk, const float* grad
       else { if (pk) launch(k_photo_bwd<2, false, true>, photo_bwd_smem<2>()); else launch(k_photo_bwd<2, false, false>, photo_bwd_smem<2>()); }
     }
   }
-  k_pose_final<<<P.B * P.N, kThreads, 0, st>>>(P, Wk.pose_part, grad_T);
+  const int unpack_chunks = grad_srcs ? div_up(P.HW, kUnpackPix) : 0;
+  k_pose_final<<<P.B * P.N * (1 + unpack_chunks), kThreads, 0, st>>>(P, Wk.pose_part, grad_T, Wk.gsrc4, grad_srcs, unpack_chunks);
   if (P.S > 1) {
     int lanes = 0;
     for (int k = 1; k < P.S; ++k) lanes = imax(lanes, P.h[k] * P.w[k] << (2 * (k - 1)));

@@ -101,14 +101,18 @@ template <> struct Img<false> {
   int HW;
   // the four bilinear taps of all three planes: four tap pointers, then + HW per plane (one IMAD.WIDE per load)
   __device__ __forceinline__ void load_taps(int o00, int o01, int o10, int o11, Texels& tx) const {
-    const float *p00 = p + o00, *p01 = p + o01, *p10 = p + o10, *p11 = p + o11;
+    // The frame base is made opaque to the optimiser: otherwise it folds the 64-bit frame offset into every
+    // address (4 integer instructions per load); with a materialised base each tap is one IMAD.WIDE and each
+    // further plane one more.
+    const float* fb = p;
+    asm volatile("" : "+l"(fb));
+    const unsigned u00 = o00, u01 = o01, u10 = o10, u11 = o11, hw = HW;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      tx.i00[c] = __ldg(p00);
-      tx.i01[c] = __ldg(p01);
-      tx.i10[c] = __ldg(p10);
-      tx.i11[c] = __ldg(p11);
-      p00 += HW; p01 += HW; p10 += HW; p11 += HW;
+    for (int c = 0; c < 3; ++c) {       // 32-bit offset add, then one widening multiply-add onto the base
+      tx.i00[c] = __ldg(fb + (u00 + c * hw));
+      tx.i01[c] = __ldg(fb + (u01 + c * hw));
+      tx.i10[c] = __ldg(fb + (u10 + c * hw));
+      tx.i11[c] = __ldg(fb + (u11 + c * hw));
     }
   }
   __device__ __forceinline__ void load3(int off, float (&v)[3]) const {
@@ -163,23 +167,7 @@ __device__ __forceinline__ void warp_sample(const KP& P, const Img<PK>& src, con
   g = reproject_ray(rx, ry, D, cam, pose, P.W, P.H, P.eps_proj, P.z_min);
   t = make_taps(g.u, g.v, P.W, P.H);
   const int r0 = t.y0 * P.W, r1 = t.y1 * P.W;
-  if constexpr (PK) {
-    src.load_taps(r0 + t.x0, r0 + t.x1, r1 + t.x0, r1 + t.x1, tx);
-  } else {
-    // one IMAD.WIDE per address: four tap pointers, then + HW (a constant-bank operand) per channel plane
-    const float* p00 = src.p + (r0 + t.x0);
-    const float* p01 = src.p + (r0 + t.x1);
-    const float* p10 = src.p + (r1 + t.x0);
-    const float* p11 = src.p + (r1 + t.x1);
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      tx.i00[c] = __ldg(p00);
-      tx.i01[c] = __ldg(p01);
-      tx.i10[c] = __ldg(p10);
-      tx.i11[c] = __ldg(p11);
-      p00 += P.HW; p01 += P.HW; p10 += P.HW; p11 += P.HW;
-    }
-  }
+  src.load_taps(r0 + t.x0, r0 + t.x1, r1 + t.x0, r1 + t.x1, tx);
 #pragma unroll
   for (int c = 0; c < 3; ++c) x[c] = bilerp(tx.i00[c], tx.i01[c], tx.i10[c], tx.i11[c], t.wx, t.wy);
 }
@@ -210,6 +198,16 @@ __device__ __forceinline__ float sample_plane(const float* __restrict__ plane, c
   d[2] = __ldg(plane + (r1 + t.x0));
   d[3] = __ldg(plane + (r1 + t.x1));
   return bilerp(d[0], d[1], d[2], d[3], t.wx, t.wy);
+}
+
+// fire-and-forget float add to GLOBAL memory (RED.E.ADD.F32): explicit address space, so that a base pointer hidden
+// from the optimiser (see Img<false>::load_taps) does not turn into a generic atomic
+__device__ __forceinline__ void red_add(float* p, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;\n" ::"l"(p), "f"(v) : "memory");
+}
+// the same for a 16-byte texel (REDG.E.ADD.F32x4): one request for the three channels of a tap
+__device__ __forceinline__ void red_add3(float4* p, float a, float b, float c) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(0.f) : "memory");
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -280,6 +278,8 @@ struct FwdBuffers {
 struct BwdBuffers {
   float* dDhat[kMaxS];   // k >= 1: [B,H,W] full-resolution depth adjoint before the up-sample adjoint
   double* pose_part;     // [B*tiles][N*12]
+  float4* gsrc4;         // [B,N,H,W] texel-interleaved gradient of the sources: the scatter target (one vector RED per
+                         // tap), unpacked into the planar grad_srcs by k_depth_gather's launch
 };
 struct SavedView {       // the caller-owned `saved` buffer, carved
   double* frame;         // [B*N*S][kSavedPerFrame]

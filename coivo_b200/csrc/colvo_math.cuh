@@ -125,8 +125,8 @@ CV_HD Taps make_taps(float u, float v, int W, int H) {
   float xf = floorf(uc), yf = floorf(vc);
   t.wx = uc - xf;
   t.wy = vc - yf;
-  t.x0 = imin(imax((int)xf, 0), W - 1);
-  t.y0 = imin(imax((int)yf, 0), H - 1);
+  t.x0 = (int)xf;          // uc is already clamped to [0, W-1] (NaN -> 0, +-inf -> the border): no integer clamp needed
+  t.y0 = (int)yf;
   t.x1 = imin(t.x0 + 1, W - 1);
   t.y1 = imin(t.y0 + 1, H - 1);
   return t;

@@ -14,8 +14,11 @@
 #pragma once
 #include "colvo_kernels.cuh"
 
+#ifndef COLVO_FWD_M_SMEM     // 1: park the target window moments in shared memory between scales (66 KB per CTA, 3 CTAs / SM);
+#define COLVO_FWD_M_SMEM 1   // 0: recompute them in every scale's walk (50 KB per CTA, 4 CTAs / SM)
+#endif
 #ifndef COLVO_MINB_FWD
-#define COLVO_MINB_FWD 3
+#define COLVO_MINB_FWD (COLVO_FWD_M_SMEM ? 3 : 4)
 #endif
 
 namespace colvo {
@@ -29,7 +32,9 @@ template <int NS>
 struct FwdSmem {
   float4 y[kDN];                            // target tile (y0, y1, y2, -)
   float4 x[2][NS][kDN];                     // double-buffered frames of one scale (or the raw sources)
+#if COLVO_FWD_M_SMEM
   float4 m[2][kFwdTileH * 32];              // per window: (mu_y[3], var_y[0]), (var_y[1], var_y[2], best identity pe, its index)
+#endif
   double red[kFwdWarps * (1 + NS * kMaxS * 2)];
 };
 
@@ -225,6 +230,10 @@ __global__ void __launch_bounds__(kFwdThreads, COLVO_MINB_FWD)
   const int trow0 = wid * kFwdRows;           // first window row of this warp = its first data row in the tile
 
   // ---- identity candidates (raw sources, a = 1, b = 0; oracle A10) and the target window moments ----
+#if !COLVO_FWD_M_SMEM
+  float id_best[kFwdRows];
+  int id_sel[kFwdRows];
+#endif
   {
     RowH<NS> R[3];
     RowY Y[3];
@@ -256,9 +265,14 @@ __global__ void __launch_bounds__(kFwdThreads, COLVO_MINB_FWD)
           const float pe = pe_value(Sx[n], Sxx[n], Sxy[n], R[(j - 1) % 3].xc[n], wy, 1.0f, 0.0f, alpha, c1, c2);
           if (pe < best) { best = pe; sel = n; }
         }
+#if COLVO_FWD_M_SMEM
         const int w = (trow0 + j - 2) * 32 + lane;
         sm.m[0][w] = make_float4(wy.muy[0], wy.muy[1], wy.muy[2], wy.sgy[0]);
         sm.m[1][w] = make_float4(wy.sgy[1], wy.sgy[2], best, __int_as_float(sel));
+#else
+        id_best[j - 2] = best;
+        id_sel[j - 2] = sel;
+#endif
       }
     }
   }
@@ -284,16 +298,28 @@ __global__ void __launch_bounds__(kFwdThreads, COLVO_MINB_FWD)
 #pragma unroll
     for (int j = 0; j < kFwdRows + 2; ++j) {
       const int o = (trow0 + j) * kDW + lane;
-      row_sums<NS, false>(R[j % 3], Y[j % 3], sm.y + o, sm.x[buf][0] + o, sm.x[buf][NS - 1] + o);
+      row_sums<NS, !COLVO_FWD_M_SMEM>(R[j % 3], Y[j % 3], sm.y + o, sm.x[buf][0] + o, sm.x[buf][NS - 1] + o);
       if (j >= 2) {
         const int wr = trow0 + j - 2, py = y0 + wr;
         if (py < P.H && col_in) {
-          const float4 m0 = sm.m[0][wr * 32 + lane], m1 = sm.m[1][wr * 32 + lane];
           WinY wy;
+#if COLVO_FWD_M_SMEM
+          const float4 m0 = sm.m[0][wr * 32 + lane], m1 = sm.m[1][wr * 32 + lane];
           wy.muy[0] = m0.x; wy.muy[1] = m0.y; wy.muy[2] = m0.z;
           wy.sgy[0] = m0.w; wy.sgy[1] = m1.x; wy.sgy[2] = m1.y;
           float best = m1.z;
           int sel = __float_as_int(m1.w);
+#else
+          float best = id_best[j - 2];
+          int sel = id_sel[j - 2];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float sy = Y[0].sy[c] + Y[1].sy[c] + Y[2].sy[c];
+            const float syy = Y[0].syy[c] + Y[1].syy[c] + Y[2].syy[c];
+            wy.muy[c] = sy * (1.0f / 9.0f);
+            wy.sgy[c] = fmaf(-wy.muy[c], wy.muy[c], syy * (1.0f / 9.0f));
+          }
+#endif
           float Sx[NS][3], Sxx[NS][3], Sxy[NS][3];
 #pragma unroll
           for (int c = 0; c < 3; ++c) {

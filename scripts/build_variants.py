@@ -5,10 +5,10 @@ from coivo_b200 import _lib
 
 VARIANTS = {
     "base": [],
-    "bpf": ["COLVO_BWD_PREFETCH=1"],
-    "bpf2": ["COLVO_BWD_PREFETCH=1", "COLVO_MINB_BWD=2"],
-    "b2": ["COLVO_MINB_BWD=2"],
-    "f2": ["COLVO_MINB_FWD=2"],
+    "nobar": ["COLVO_EXP_NOBAR=1"],
+    "nogather": ["COLVO_EXP_NOGATHER=1"],
+    "nored": ["COLVO_EXP_NORED=1"],
+    "noall": ["COLVO_EXP_NORED=1", "COLVO_EXP_NOGATHER=1", "COLVO_EXP_NOBAR=1"],
 }
 out = os.path.join(os.path.dirname(_lib.PKG_DIR), "build", "variants")
 os.makedirs(out, exist_ok=True)
