@@ -80,7 +80,6 @@ size_t carve_fwd(const ColvoDesc* d, void* ws, FwdBuffers& F) {
   F.stat_chunks = stat_chunks(d);
   F.stat_part = c.take<double>(BNS * F.stat_chunks * kStatVals);
   F.smooth_part = c.take<double>((size_t)d->B * smooth_tiles(d) * kSmVals);
-  F.smooth_bk = c.take<double>((size_t)d->B * d->S * kSmVals);
   F.loss_part = c.take<double>((size_t)d->B * tiles);
   F.g_part = c.take<double>((size_t)d->B * tiles * d->N * kMaxS * 2);
   F.iw = c.take<float4>(BNS * (size_t)d->H * d->W);

@@ -168,6 +168,9 @@ __global__ void __launch_bounds__(kThreads)
     block_reduce_store<kSmVals, double>(accd, red, O.part + ((long long)blk * P.S + k) * kSmVals);
     __syncthreads();          // red is reused by the next scale
   }
+  // launched programmatically behind k_photo_fwd, whose results it does not need: it fills that kernel's tail.
+  // k_finalize_fwd needs both, so this grid must not complete before its predecessor has.
+  pdl_wait();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -182,6 +185,7 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_STATS)
   constexpr int NA = GEO ? kStatVals : 5;      // accumulators per source (the 6th only with the geometric term)
   constexpr int NV = NA * NS;
   __shared__ double sm[(kThreads / 32) * NV];
+  pdl_trigger();                               // k_lcc_solve / k_photo_fwd may start their prologues in this kernel's tail
   const int bk = blockIdx.y, k = bk % P.S, b = bk / P.S;
   const Cam cam = load_cam(P, b);
   const float* Dk = P.depth[k] + (long long)b * P.depth_bs[k];
@@ -258,25 +262,10 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_STATS)
 
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32)
-    k_lcc_solve(KP P, const double* __restrict__ part, int chunks, float* __restrict__ ab, double* __restrict__ saved,
-                const double* __restrict__ smooth_part, double* __restrict__ smooth_bk) {
+    k_lcc_solve(KP P, const double* __restrict__ part, int chunks, float* __restrict__ ab, double* __restrict__ saved) {
   const int bnk = blockIdx.x, lane = threadIdx.x;
-  if (bnk >= P.B * P.N * P.S) {        // extra blocks: the smoothness partials of (b, k), summed in a fixed order
-    const int bk = bnk - P.B * P.N * P.S, b = bk / P.S, k = bk - b * P.S;
-    const double* sp = smooth_part + ((long long)b * P.sm_blocks * P.S + k) * kSmVals;
-    double v[kSmVals] = {0.0, 0.0, 0.0, 0.0};
-    for (int t = lane; t < P.sm_blocks; t += 32) {
-#pragma unroll
-      for (int j = 0; j < kSmVals; ++j) v[j] += sp[(long long)t * P.S * kSmVals + j];
-    }
-#pragma unroll
-    for (int j = 0; j < kSmVals; ++j) v[j] = warp_sum(v[j]);
-    if (lane == 0) {
-#pragma unroll
-      for (int j = 0; j < kSmVals; ++j) smooth_bk[bk * kSmVals + j] = v[j];
-    }
-    return;
-  }
+  pdl_trigger();
+  pdl_wait();                          // the statistics partials of k_warp_stats
   double s[5] = {0, 0, 0, 0, 0};
   if (P.flags & 1u) {
     for (int c = lane; c < chunks; c += 32) {
@@ -382,7 +371,7 @@ __device__ __forceinline__ void ywin_init(YWin& y, const float* ys, int own) {
 // blocks [1+BNS, 1+BNS+B*S): mean inverse depth and sum_p s_p d_p of (b, k) for the smoothness adjoint.
 __global__ void __launch_bounds__(kThreads)
     k_finalize_fwd(KP P, const double* __restrict__ loss_part, const double* __restrict__ g_part,
-                   const double* __restrict__ smooth_bk, const double* __restrict__ stat_part, int stat_chunks,
+                   const double* __restrict__ smooth_part, const double* __restrict__ stat_part, int stat_chunks,
                    float* __restrict__ loss, double* __restrict__ saved_frame, double* __restrict__ saved_scale,
                    int need_g) {
   __shared__ double sm[(kThreads / 32) * 2];
@@ -410,12 +399,25 @@ __global__ void __launch_bounds__(kThreads)
       const double wg = (double)P.geo_weight / ((double)P.B * (double)P.N * (double)P.HW);
       for (int i = threadIdx.x; i < BNS * stat_chunks; i += kThreads) acc[1] += stat_part[(long long)i * kStatVals + 5] * wg;
     }
-    // smoothness: per-(b, k) sums (k_lcc_solve's extra blocks), normalised by 1 / (mean d + eps) (see k_smooth)
-    for (int bk = threadIdx.x; bk < P.B * P.S; bk += kThreads) {
-      const int k = bk % P.S;
-      const double* v = smooth_bk + bk * kSmVals;
-      const double mean = v[3] / ((double)P.h[k] * (double)P.w[k]);
-      acc[1] += (v[0] * wk_s[k][0] + v[1] * wk_s[k][1]) / (mean + (double)P.eps_disp);
+    // smoothness: one warp per (b, k) sums the partials of that image's k_smooth CTAs, then applies
+    // 1 / (mean d + eps) (see k_smooth)
+    {
+      double sm_acc = 0.0;
+      for (int bk = wid; bk < P.B * P.S; bk += kThreads / 32) {
+        const int b = bk / P.S, k = bk - b * P.S;
+        const double* sp = smooth_part + ((long long)b * P.sm_blocks * P.S + k) * kSmVals;
+        double sx = 0.0, sy = 0.0, sd = 0.0;
+        for (int t = lane; t < P.sm_blocks; t += 32) {
+          const double* q = sp + (long long)t * P.S * kSmVals;
+          sx += q[0];
+          sy += q[1];
+          sd += q[3];
+        }
+        sx = warp_sum(sx); sy = warp_sum(sy); sd = warp_sum(sd);
+        const double mean = sd / ((double)P.h[k] * (double)P.w[k]);
+        sm_acc += (sx * wk_s[k][0] + sy * wk_s[k][1]) / (mean + (double)P.eps_disp);
+      }
+      if (lane == 0) acc[1] += sm_acc;
     }
     for (int j = 0; j < 2; ++j) {
       double s = warp_sum(acc[j]);
@@ -455,10 +457,21 @@ __global__ void __launch_bounds__(kThreads)
     return;
   }
   // mean inverse depth and sum_p s_p d_p of (b, k), for the smoothness adjoint
-  const int bk = blockIdx.x - 1 - BNS, k = bk % P.S;
-  if (threadIdx.x == 0) {
-    saved_scale[bk * kSavedPerScale + 0] = smooth_bk[bk * kSmVals + 3] / ((double)P.h[k] * (double)P.w[k]);
-    saved_scale[bk * kSavedPerScale + 1] = smooth_bk[bk * kSmVals + 2];
+  const int bk = blockIdx.x - 1 - BNS, b = bk / P.S, k = bk - b * P.S;
+  if (threadIdx.x < 32) {
+    const double* sp = smooth_part + ((long long)b * P.sm_blocks * P.S + k) * kSmVals;
+    double s = 0.0, sd = 0.0;
+    for (int t = lane; t < P.sm_blocks; t += 32) {
+      const double* q = sp + (long long)t * P.S * kSmVals;
+      s += q[2];
+      sd += q[3];
+    }
+    s = warp_sum(s);
+    sd = warp_sum(sd);
+    if (lane == 0) {
+      saved_scale[bk * kSavedPerScale + 0] = sd / ((double)P.h[k] * (double)P.w[k]);
+      saved_scale[bk * kSavedPerScale + 1] = s;
+    }
   }
 }
 
@@ -542,18 +555,6 @@ cudaError_t launch_forward(const KP& P, const FwdBuffers& Wk, float* loss, float
   const int BNS = P.B * P.N * P.S;
   const bool pk = (P.flags & 16u) != 0;
   {
-    SmoothOut smo;
-    smo.part = Wk.smooth_part;
-    for (int k = 0; k < kMaxS; ++k) smo.sf[k] = save ? sv.s_field[k] : nullptr;
-    const size_t smem = sizeof(float) * (sm_img_floats() + ((sm_dep_floats() + 1) & ~1)) + sizeof(double) * (kThreads / 32) * kSmVals;
-    dim3 g(div_up(P.W, kSmBW), div_up(P.H, kSmBH), P.B);
-    auto run = [&](auto kern) {
-      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      kern<<<g, kThreads, smem, st>>>(P, smo);
-    };
-    if (pk) run(k_smooth<true>); else run(k_smooth<false>);
-  }
-  {
     ScopedKernelTimer tm(3, st);
     dim3 g(Wk.stat_chunks, P.B * P.S);
     const bool geo = P.src_depth != nullptr;
@@ -566,8 +567,9 @@ cudaError_t launch_forward(const KP& P, const FwdBuffers& Wk, float* loss, float
       else { if (pk) run(k_warp_stats<2, false, true>); else run(k_warp_stats<2, false, false>); }
     }
   }
-  k_lcc_solve<<<BNS + P.B * P.S, 32, 0, st>>>(P, Wk.stat_part, Wk.stat_chunks, ab, save ? sv.frame : nullptr, Wk.smooth_part,
-                                              Wk.smooth_bk);
+  cudaError_t e = launch_pdl(k_lcc_solve, dim3(BNS), dim3(32), 0, st, P, Wk.stat_part, Wk.stat_chunks, ab,
+                             save ? sv.frame : nullptr);
+  if (e != cudaSuccess) return e;
   dim3 grid(P.ftiles_x, P.ftiles_y, P.B);
   {
     ScopedKernelTimer tm(1, st);
@@ -575,13 +577,27 @@ cudaError_t launch_forward(const KP& P, const FwdBuffers& Wk, float* loss, float
     // opting in to > 48 KB of dynamic shared memory is a per-function, per-device attribute: cheap and idempotent
     auto run = [&](auto kern, size_t smem) {
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      kern<<<grid, kFwdThreads, smem, st>>>(P, ab, sel, Wk.loss_part, Wk.g_part, need_g, co, Wk.iw);
+      e = launch_pdl(kern, grid, dim3(kFwdThreads), smem, st, P, ab, sel, Wk.loss_part, Wk.g_part, need_g, co, Wk.iw);
     };
     if (P.N == 1) { if (pk) run(k_photo_fwd<1, true>, photo_fwd_smem<1>()); else run(k_photo_fwd<1, false>, photo_fwd_smem<1>()); }
     else { if (pk) run(k_photo_fwd<2, true>, photo_fwd_smem<2>()); else run(k_photo_fwd<2, false>, photo_fwd_smem<2>()); }
   }
+  if (e != cudaSuccess) return e;
+  {
+    SmoothOut smo;
+    smo.part = Wk.smooth_part;
+    for (int k = 0; k < kMaxS; ++k) smo.sf[k] = save ? sv.s_field[k] : nullptr;
+    const size_t smem = sizeof(float) * (sm_img_floats() + ((sm_dep_floats() + 1) & ~1)) + sizeof(double) * (kThreads / 32) * kSmVals;
+    dim3 g(div_up(P.W, kSmBW), div_up(P.H, kSmBH), P.B);
+    auto run = [&](auto kern) {
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      e = launch_pdl(kern, g, dim3(kThreads), smem, st, P, smo);
+    };
+    if (pk) run(k_smooth<true>); else run(k_smooth<false>);
+  }
+  if (e != cudaSuccess) return e;
   const int nfin = 1 + (save ? BNS + P.B * P.S : 0);
-  k_finalize_fwd<<<nfin, kThreads, 0, st>>>(P, Wk.loss_part, Wk.g_part, Wk.smooth_bk, Wk.stat_part, Wk.stat_chunks,
+  k_finalize_fwd<<<nfin, kThreads, 0, st>>>(P, Wk.loss_part, Wk.g_part, Wk.smooth_part, Wk.stat_part, Wk.stat_chunks,
                                             loss, sv.frame, sv.scale, need_g);
   return cudaGetLastError();
 }
@@ -589,7 +605,7 @@ cudaError_t launch_forward(const KP& P, const FwdBuffers& Wk, float* loss, float
 cudaError_t launch_consistency(const KP& P, double* stat_part, int stat_chunks, double* pe_part, float* ab, float* out,
                                cudaStream_t st) {
   k_warp_stats<1, false, false><<<dim3(stat_chunks, P.B), kThreads, 0, st>>>(P, stat_part, nullptr, nullptr, nullptr);
-  k_lcc_solve<<<P.B, 32, 0, st>>>(P, stat_part, stat_chunks, ab, nullptr, nullptr, nullptr);
+  k_lcc_solve<<<P.B, 32, 0, st>>>(P, stat_part, stat_chunks, ab, nullptr);
   k_consistency_pe<<<dim3(P.tiles_x, P.tiles_y, P.B), kThreads, 0, st>>>(P, ab, pe_part);
   k_consistency_final<<<P.B, kThreads, 0, st>>>(P, pe_part, ab, out);
   return cudaGetLastError();

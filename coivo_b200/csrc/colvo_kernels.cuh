@@ -210,6 +210,29 @@ __device__ __forceinline__ void red_add3(float4* p, float a, float b, float c) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(0.f) : "memory");
 }
 
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization attribute
+// may start while its predecessor in the stream is still draining; pdl_wait() blocks until the predecessor grid has
+// completed and its writes are visible, pdl_trigger() lets the successor's CTAs be scheduled early.  Both are
+// no-ops for a normally launched kernel.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;\n" ::); }
+
+// launch `kern` so that it may overlap the tail of the previous kernel in `st` (see pdl_wait)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg;
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -270,7 +293,6 @@ struct FwdBuffers {
   double* stat_part;     // [B*N*S][stat_chunks][kStatVals]
   int stat_chunks;
   double* smooth_part;   // [B][sm_blocks][S][kSmVals] per k_smooth CTA and scale: sum_x, sum_y, sum s*d, sum d (un-normalised)
-  double* smooth_bk;     // [B*S][kSmVals]            the same, summed per (b, k) by the extra blocks of k_lcc_solve
   double* loss_part;     // [B*tiles]
   double* g_part;        // [B*tiles][N*kMaxS*2]
   float4* iw;            // [B,N,S,H,W] raw warped frames as (x0, x1, x2, -) texels (k_warp_stats -> k_photo_fwd)

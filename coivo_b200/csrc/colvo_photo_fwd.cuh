@@ -221,9 +221,9 @@ __global__ void __launch_bounds__(kFwdThreads, COLVO_MINB_FWD)
     }
   }
   cp_async_commit();
-  stage_scale(0, 1);
   for (int i = tid; i < kFwdWarps * NV; i += kFwdThreads) sm.red[i] = 0.0;   // slots of unused scales stay 0
-  cp_async_wait_but_one();      // the raw frames have landed; scale 0 may still be in flight
+  pdl_trigger();                // k_smooth (independent work) may fill this kernel's tail
+  cp_async_wait_all();          // the raw frames have landed
   __syncthreads();
 
   const float alpha = P.alpha, c1 = P.c1, c2 = P.c2;
@@ -277,6 +277,10 @@ __global__ void __launch_bounds__(kFwdThreads, COLVO_MINB_FWD)
     }
   }
 
+  // Everything above depends on the inputs only: launched programmatically, this CTA may have run it in the tail of
+  // k_warp_stats.  The warped frames and (a, b) are needed from here on.
+  pdl_wait();
+  stage_scale(0, 1);
   float loss_acc = 0.f;
 #pragma unroll 1
   for (int k = 0; k < P.S; ++k) {
