@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_BWD)
   float (*pose_s)[12] = reinterpret_cast<float (*)[12]>(cst + NS);                                   // [NS]: R row-major, t
   float* cst_sm = reinterpret_cast<float*>(pose_s + NS);   // scale 0: 1/(mean+eps), sum(s d)/(n (mean+eps)^2)
 
+  pdl_trigger();         // the epilogue launch may become resident while this kernel drains
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
   const int b = blockIdx.z, x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
   const int px = x0 + tx, py = y0 + ty;
@@ -305,11 +306,22 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_BWD)
 // The blocks beyond B*N unpack the texel-interleaved source gradient into the planar grad_srcs [B,N,3,H,W]
 // (kUnpackPix pixels of one (b,n) frame each; independent of the pose reduction, so it shares the launch).
 constexpr int kUnpackPix = 4 * kThreads;
-__global__ void __launch_bounds__(kThreads)
-    k_pose_final(KP P, const double* __restrict__ pose_part, float* __restrict__ grad_T,
-                 const float4* __restrict__ gsrc4, float* __restrict__ grad_srcs, int unpack_chunks) {
-  if ((int)blockIdx.x >= P.B * P.N) {
-    const int j = blockIdx.x - P.B * P.N, bn = j / unpack_chunks, c = j - bn * unpack_chunks;
+struct PoseFinalArgs {
+  const double* pose_part;
+  float* grad_T;
+  const float4* gsrc4;
+  float* grad_srcs;
+  int unpack_chunks;
+  int n_blocks;          // B*N pose blocks + B*N*unpack_chunks unpack blocks
+};
+__device__ __forceinline__ void pose_final_block(const KP& P, const PoseFinalArgs& A, int blk) {
+  const double* __restrict__ pose_part = A.pose_part;
+  float* __restrict__ grad_T = A.grad_T;
+  const float4* __restrict__ gsrc4 = A.gsrc4;
+  float* __restrict__ grad_srcs = A.grad_srcs;
+  const int unpack_chunks = A.unpack_chunks;
+  if (blk >= P.B * P.N) {
+    const int j = blk - P.B * P.N, bn = j / unpack_chunks, c = j - bn * unpack_chunks;
     const float4* src = gsrc4 + (long long)bn * P.HW;
     float* dst = grad_srcs + (long long)bn * 3 * P.HW;
 #pragma unroll
@@ -324,7 +336,7 @@ __global__ void __launch_bounds__(kThreads)
     }
     return;
   }
-  const int bn = blockIdx.x, b = bn / P.N, n = bn % P.N;
+  const int bn = blk, b = bn / P.N, n = bn % P.N;
   const int tiles = P.tiles_x * P.tiles_y, nv = P.N * 12;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   for (int j = wid; j < 16; j += kThreads / 32) {
@@ -343,6 +355,11 @@ __global__ void __launch_bounds__(kThreads)
   }
 }
 
+__global__ void __launch_bounds__(kThreads) k_pose_final(KP P, PoseFinalArgs A) {
+  pdl_wait();            // launched programmatically behind k_photo_bwd
+  pose_final_block(P, A, blockIdx.x);
+}
+
 // ------------------------------------------------------------------------------------------
 // Adjoint of upsample_depth in gather form: low-res texel (i, j) sums every full-res pixel whose
 // 2x2 bilinear footprint contains it.  4^(k-1) lanes share one texel (its footprint grows as 4^k)
@@ -352,7 +369,13 @@ __global__ void __launch_bounds__(kThreads)
     k_depth_gather(KP P, const float* __restrict__ grad_loss, const double* __restrict__ saved_scale,
                    const float* __restrict__ dD1, const float* __restrict__ dD2, const float* __restrict__ dD3,
                    const float* __restrict__ sf1, const float* __restrict__ sf2, const float* __restrict__ sf3,
-                   float* g1, float* g2, float* g3) {
+                   float* g1, float* g2, float* g3, PoseFinalArgs A) {
+  pdl_wait();            // launched programmatically behind k_photo_bwd
+  if ((int)blockIdx.y >= P.B * (P.S - 1)) {     // the grid rows beyond the (b, k) pairs: pose reduction and source-gradient unpack
+    const int j = ((int)blockIdx.y - P.B * (P.S - 1)) * gridDim.x + blockIdx.x;
+    if (j < A.n_blocks) pose_final_block(P, A, j);
+    return;
+  }
   const int b = blockIdx.y / (P.S - 1), k = blockIdx.y % (P.S - 1) + 1;
   const int hk = P.h[k], wk = P.w[k], n = hk * wk;
   const int G = 1 << (k - 1), L = G * G;            // lanes per texel
@@ -450,15 +473,27 @@ cudaError_t launch_backward(const KP& P, const BwdBuffers& Wk, const float* grad
       else { if (pk) launch(k_photo_bwd<2, false, true>, photo_bwd_smem<2>()); else launch(k_photo_bwd<2, false, false>, photo_bwd_smem<2>()); }
     }
   }
-  const int unpack_chunks = grad_srcs ? div_up(P.HW, kUnpackPix) : 0;
-  k_pose_final<<<P.B * P.N * (1 + unpack_chunks), kThreads, 0, st>>>(P, Wk.pose_part, grad_T, Wk.gsrc4, grad_srcs, unpack_chunks);
+  // epilogue: pose reduction, source-gradient unpack and the up-sample adjoint are independent of each other, so they
+  // share one launch (programmatic, so its CTAs are resident by the time k_photo_bwd drains)
+  PoseFinalArgs A;
+  A.pose_part = Wk.pose_part;
+  A.grad_T = grad_T;
+  A.gsrc4 = Wk.gsrc4;
+  A.grad_srcs = grad_srcs;
+  A.unpack_chunks = grad_srcs ? div_up(P.HW, kUnpackPix) : 0;
+  A.n_blocks = P.B * P.N * (1 + A.unpack_chunks);
   if (P.S > 1) {
     int lanes = 0;
     for (int k = 1; k < P.S; ++k) lanes = imax(lanes, P.h[k] * P.w[k] << (2 * (k - 1)));
-    k_depth_gather<<<dim3(div_up(lanes, kThreads), P.B * (P.S - 1)), kThreads, 0, st>>>(
-        P, grad_loss, sv.scale, Wk.dDhat[1], Wk.dDhat[2], Wk.dDhat[3], sv.s_field[1], sv.s_field[2], sv.s_field[3],
-        grad_depth[1], P.S > 2 ? grad_depth[2] : nullptr, P.S > 3 ? grad_depth[3] : nullptr);
+    const int gx = div_up(lanes, kThreads);
+    e = launch_pdl(k_depth_gather, dim3(gx, P.B * (P.S - 1) + div_up(A.n_blocks, gx)), dim3(kThreads), 0, st, P, grad_loss,
+                   (const double*)sv.scale, (const float*)Wk.dDhat[1], (const float*)Wk.dDhat[2], (const float*)Wk.dDhat[3],
+                   (const float*)sv.s_field[1], (const float*)sv.s_field[2], (const float*)sv.s_field[3], grad_depth[1],
+                   P.S > 2 ? grad_depth[2] : nullptr, P.S > 3 ? grad_depth[3] : nullptr, A);
+  } else {
+    e = launch_pdl(k_pose_final, dim3(A.n_blocks), dim3(kThreads), 0, st, P, A);
   }
+  if (e != cudaSuccess) return e;
   return cudaGetLastError();
 }
 
