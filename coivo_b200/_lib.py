@@ -98,6 +98,8 @@ _SIGS = {
     "colvo_consistency": (ctypes.c_int, [ctypes.c_int32] * 3 + [ctypes.c_uint32, _vp, _vp, _vp, _vp, ctypes.c_int32,
                                                                  _vp, _vp, ctypes.c_size_t, _vp]),
     "colvo_step_host_arena_bytes": (ctypes.c_int, [ctypes.POINTER(ColvoDesc), ctypes.POINTER(ctypes.c_size_t)]),
+    "colvo_step_host_arena_grads": (ctypes.c_int, [ctypes.POINTER(ColvoDesc), ctypes.POINTER(ctypes.c_size_t),
+                                                   ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_size_t)]),
     "colvo_photo_step_host": (ctypes.c_int, [ctypes.POINTER(ColvoDesc), _vp, _vp, ctypes.POINTER(_vp), _vp, _vp, _vp,
                                              ctypes.POINTER(_vp), _vp, _vp, ctypes.c_float, _vp, ctypes.c_size_t, _vp]),
     "colvo_debug_time_kernel": (ctypes.c_int, [ctypes.c_int, _vp, _vp]),
@@ -114,8 +116,8 @@ EXPORTS = tuple(_SIGS)
 
 K_PHOTO_FWD, K_PHOTO_BWD, K_WARP_STATS = 1, 2, 3
 # kernels launched by one forward + one backward (S > 1, LCC on); bench.py's gpu_launches
-KERNELS_FWD = ("k_prepass", "k_warp_stats", "k_lcc_solve", "k_photo_fwd", "k_smooth_fwd", "k_finalize_fwd")
-KERNELS_BWD = ("k_photo_bwd", "k_pose_final", "k_depth_gather")
+KERNELS_FWD = ("k_warp_stats", "k_lcc_solve", "k_photo_fwd", "k_smooth", "k_finalize_fwd")
+KERNELS_BWD = ("k_photo_bwd", "k_depth_gather")      # (k_depth_gather's launch carries the pose reduction and the unpack)
 
 
 def load(auto_build: bool = True) -> ctypes.CDLL:

@@ -329,18 +329,32 @@ int colvo_step_host_arena_bytes(const ColvoDesc* d, size_t* bytes) {
   return 0;
 }
 
+int colvo_step_host_arena_grads(const ColvoDesc* d, size_t* grad_depth_off, size_t* grad_T_off, size_t* grad_srcs_off) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  if (!grad_depth_off || !grad_T_off || !grad_srcs_off) return COLVO_E_NULL_PTR;
+  Arena A;
+  carve_arena(d, reinterpret_cast<void*>(uintptr_t(256)), A);     // carve at a dummy aligned base: offsets = pointer - base
+  const char* base = reinterpret_cast<const char*>(uintptr_t(256));
+  for (int k = 0; k < d->S; ++k) grad_depth_off[k] = (size_t)(reinterpret_cast<const char*>(A.grad_depth[k]) - base);
+  *grad_T_off = (size_t)(reinterpret_cast<const char*>(A.grad_T) - base);
+  *grad_srcs_off = (size_t)(reinterpret_cast<const char*>(A.grad_srcs) - base);
+  return 0;
+}
+
 int colvo_photo_step_host(const ColvoDesc* d_in, const float* h_tgt, const float* h_srcs, const float* const* h_depth,
                           const float* h_K, const float* h_T, float* h_loss, float* const* h_grad_depth,
                           float* h_grad_T, float* h_grad_srcs, float grad_scale, void* arena, size_t arena_bytes,
                           void* stream) {
   int rc = check_desc(d_in);
   if (rc) return rc;
-  if (!h_tgt || !h_srcs || !h_depth || !h_K || !h_T || !h_loss || !h_grad_depth || !h_grad_T || !arena)
-    return COLVO_E_NULL_PTR;
+  if (!h_tgt || !h_srcs || !h_depth || !h_K || !h_T || !h_loss || !arena) return COLVO_E_NULL_PTR;
+  const bool grads_to_host = h_grad_depth != nullptr;     // NULL: the gradients stay in the device arena
+  if (grads_to_host && !h_grad_T) return COLVO_E_NULL_PTR;
   ColvoDesc d = *d_in;
   d.flags |= COLVO_F_SAVE_FOR_BWD;
   const bool want_src = !(d.flags & COLVO_F_NO_SRC_GRAD);
-  if (want_src && !h_grad_srcs) return COLVO_E_NULL_PTR;
+  if (grads_to_host && want_src && !h_grad_srcs) return COLVO_E_NULL_PTR;
   if ((uintptr_t)arena & 255u) return COLVO_E_MISALIGNED;
   Arena A;
   if (carve_arena(&d, arena, A) > arena_bytes) return COLVO_E_WORKSPACE;
@@ -355,7 +369,7 @@ int colvo_photo_step_host(const ColvoDesc* d_in, const float* h_tgt, const float
   CV_COPY(A.tgt, h_tgt, B * 3 * HW, cudaMemcpyHostToDevice);
   CV_COPY(A.srcs, h_srcs, B * N * 3 * HW, cudaMemcpyHostToDevice);
   for (int k = 0; k < d.S; ++k) {
-    if (!h_depth[k] || !h_grad_depth[k]) return COLVO_E_NULL_PTR;
+    if (!h_depth[k] || (grads_to_host && !h_grad_depth[k])) return COLVO_E_NULL_PTR;
     CV_COPY(A.depth[k], h_depth[k], B * d.h[k] * d.w[k], cudaMemcpyHostToDevice);
   }
   CV_COPY(A.K, h_K, B * 9, cudaMemcpyHostToDevice);
@@ -372,9 +386,11 @@ int colvo_photo_step_host(const ColvoDesc* d_in, const float* h_tgt, const float
                             want_src ? A.grad_srcs : nullptr, nullptr, A.ws, A.ws_bytes, stream);
   if (rc) return rc;
   CV_COPY(h_loss, A.loss, 1, cudaMemcpyDeviceToHost);
-  for (int k = 0; k < d.S; ++k) CV_COPY(h_grad_depth[k], A.grad_depth[k], B * d.h[k] * d.w[k], cudaMemcpyDeviceToHost);
-  CV_COPY(h_grad_T, A.grad_T, B * N * 16, cudaMemcpyDeviceToHost);
-  if (want_src) CV_COPY(h_grad_srcs, A.grad_srcs, B * N * 3 * HW, cudaMemcpyDeviceToHost);
+  if (grads_to_host) {
+    for (int k = 0; k < d.S; ++k) CV_COPY(h_grad_depth[k], A.grad_depth[k], B * d.h[k] * d.w[k], cudaMemcpyDeviceToHost);
+    CV_COPY(h_grad_T, A.grad_T, B * N * 16, cudaMemcpyDeviceToHost);
+    if (want_src) CV_COPY(h_grad_srcs, A.grad_srcs, B * N * 3 * HW, cudaMemcpyDeviceToHost);
+  }
 #undef CV_COPY
   return 0;
 }

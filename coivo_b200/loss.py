@@ -229,10 +229,18 @@ class HostStepper:
     The batch is split into `chunks` contiguous sub-batches, each on its own CUDA stream with its
     own device arena, so the H2D copy of one chunk overlaps the kernels of another and the D2H
     copy of a third (the three engines of the GPU work concurrently); gradients are those of the
-    whole-batch mean loss (each chunk runs with grad_loss = B_chunk / B)."""
+    whole-batch mean loss (each chunk runs with grad_loss = B_chunk / B).
+
+    `grads="host"` copies every gradient back to pinned host buffers; `grads="device"` leaves them in
+    the device arenas (what a training step does: the depth / pose networks consume them on the GPU)
+    and reads back the loss only -- `device_grads()` returns views of them."""
 
     def __init__(self, B, N, S, H, W, *, device="cuda:0", lcc=True, lcc_detach=False, want_src_grad=True,
-                 alpha=0.85, smooth_weight=1e-3, chunks=3):
+                 alpha=0.85, smooth_weight=1e-3, chunks=3, grads="host"):
+        if grads not in ("host", "device"):
+            raise ValueError("grads must be 'host' or 'device'")
+        self.grads = grads
+        self.N, self.H, self.W = N, H, W
         self.lib = _lib.load()
         self.device = torch.device(device)
         flags = (_lib.F_LCC if lcc else 0) | (_lib.F_LCC_DETACH if lcc_detach else 0)
@@ -266,10 +274,35 @@ class HostStepper:
         return 4 * (tgt.numel() + srcs.numel() + sum(d.numel() for d in depth) + K.numel() + pose.numel())
 
     def d2h_bytes(self) -> int:
-        n = len(self.spans) + sum(g.numel() for g in self.h_grad_depth) + self.h_grad_T.numel()
-        if self.h_grad_srcs is not None:
-            n += self.h_grad_srcs.numel()
+        n = len(self.spans)
+        if self.grads == "host":
+            n += sum(g.numel() for g in self.h_grad_depth) + self.h_grad_T.numel()
+            if self.h_grad_srcs is not None:
+                n += self.h_grad_srcs.numel()
         return 4 * n
+
+    def device_grads(self):
+        """Per chunk: `(grad_depth[S], grad_T, grad_srcs)` as views into that chunk's device arena (valid after the
+        chunk's stream has finished; overwritten by the next `step`)."""
+        out = []
+        for i, (lo, hi) in enumerate(self.spans):
+            n = hi - lo
+            offs = (ctypes.c_size_t * _lib.MAX_SCALES)()
+            oT, oS = ctypes.c_size_t(), ctypes.c_size_t()
+            _lib.check(self.lib.colvo_step_host_arena_grads(ctypes.byref(self.descs[i]), offs, ctypes.byref(oT), ctypes.byref(oS)),
+                       "colvo_step_host_arena_grads")
+            a = self.arenas[i]
+
+            def view(off, shape):
+                cnt = 1
+                for s_ in shape:
+                    cnt *= s_
+                return a[off:off + 4 * cnt].view(torch.float32).view(*shape)
+
+            gd = [view(offs[k], (n, 1, self.H >> k, self.W >> k)) for k in range(self.S)]
+            gs = view(oS.value, (n, self.N, 3, self.H, self.W)) if self.h_grad_srcs is not None else None
+            out.append((gd, view(oT.value, (n, self.N, 4, 4)), gs))
+        return out
 
     def step(self, depth, pose, K, tgt, srcs):
         """Inputs are CPU tensors (pinned for full speed).  Enqueues every chunk on its own stream, ordered
@@ -282,12 +315,14 @@ class HostStepper:
             for i, (lo, hi) in enumerate(self.spans):
                 st = self.streams[i]
                 st.wait_stream(cur)
+                to_host = self.grads == "host"
                 rc = self.lib.colvo_photo_step_host(
                     ctypes.byref(self.descs[i]), tgt[lo:hi].data_ptr(), srcs[lo:hi].data_ptr(),
                     _lib.ptr_array([d[lo:hi].data_ptr() for d in depth]), K[lo:hi].data_ptr(), pose[lo:hi].data_ptr(),
-                    self.h_loss_parts[i:i + 1].data_ptr(), _lib.ptr_array([g[lo:hi].data_ptr() for g in self.h_grad_depth]),
-                    self.h_grad_T[lo:hi].data_ptr(),
-                    self.h_grad_srcs[lo:hi].data_ptr() if self.h_grad_srcs is not None else None,
+                    self.h_loss_parts[i:i + 1].data_ptr(),
+                    _lib.ptr_array([g[lo:hi].data_ptr() for g in self.h_grad_depth]) if to_host else None,
+                    self.h_grad_T[lo:hi].data_ptr() if to_host else None,
+                    self.h_grad_srcs[lo:hi].data_ptr() if (to_host and self.h_grad_srcs is not None) else None,
                     ctypes.c_float((hi - lo) / self.B), self.arenas[i].data_ptr(), self.arenas[i].numel(), st.cuda_stream)
                 _lib.check(rc, "colvo_photo_step_host")
                 self._done[i].record(st)

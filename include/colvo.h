@@ -119,12 +119,15 @@ int colvo_consistency(int32_t F, int32_t H, int32_t W, uint32_t flags, const flo
 /* End-to-end step on HOST buffers: H2D copies of the inputs (use pinned memory), forward,
  * backward with grad_loss = grad_scale, D2H copies of loss and gradients, all on `stream`.
  * `arena` is caller-owned DEVICE memory of colvo_step_host_arena_bytes bytes.
- * h_grad_srcs may be NULL with COLVO_F_NO_SRC_GRAD.  The call does not synchronise: the host
+ * h_grad_srcs may be NULL with COLVO_F_NO_SRC_GRAD.  h_grad_depth == NULL keeps ALL gradients on the device (only
+ * the loss is read back): a training step consumes them there; colvo_step_host_arena_grads gives their byte
+ * offsets inside `arena` (grad_depth_off[S], grad_T [B,N,4,4], grad_srcs [B,N,3,H,W]).  The call does not synchronise: the host
  * outputs are complete once `stream` has been synchronised.  A caller that splits a batch into
  * chunks on several streams (to overlap H2D, compute and D2H) passes grad_scale = B_chunk / B and
  * combines the chunk losses with the same weights.
  */
 int colvo_step_host_arena_bytes(const ColvoDesc* d, size_t* bytes);
+int colvo_step_host_arena_grads(const ColvoDesc* d, size_t* grad_depth_off, size_t* grad_T_off, size_t* grad_srcs_off);
 int colvo_photo_step_host(const ColvoDesc* d, const float* h_tgt, const float* h_srcs, const float* const* h_depth,
                           const float* h_K, const float* h_T, float* h_loss, float* const* h_grad_depth,
                           float* h_grad_T, float* h_grad_srcs, float grad_scale, void* arena, size_t arena_bytes,

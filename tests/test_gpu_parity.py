@@ -193,6 +193,16 @@ def test_host_stepper_matches_device_path(chunks):
             assert relinf(st.h_grad_depth[k], gd[k]) < 1e-5
         assert relinf(st.h_grad_T, gT) < 1e-5
     assert relinf(st.h_grad_srcs, gs) < 1e-5
+    # the same step with the gradients left on the device (only the loss is read back)
+    sd = coivo_b200.HostStepper(2, 2, 4, 64, 96, device=DEV, chunks=chunks, grads="device")
+    sd.step(*[pin(x) if not isinstance(x, list) else [pin(y) for y in x] for x in (d["depth"], d["pose"], d["K"], d["tgt"], d["srcs"])])
+    l3 = sd.finish()
+    assert abs(l3.item() - loss.item()) <= 1e-6 * abs(loss.item())
+    assert sd.d2h_bytes() == 4 * len(sd.spans)
+    for (lo, hi), (gd_c, gT_c, gs_c) in zip(sd.spans, sd.device_grads()):
+        for k in range(4):
+            assert relinf(gd_c[k], gd[k][lo:hi]) < 1e-5
+        assert relinf(gT_c, gT[lo:hi]) < 1e-5 and relinf(gs_c, gs[lo:hi]) < 1e-5
     assert st.d2h_bytes() == 4 * (chunks + sum(x.numel() for x in gd) + gT.numel() + gs.numel())
 
 
