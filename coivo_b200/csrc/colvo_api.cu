@@ -67,6 +67,12 @@ void fill_params(KP& P, const ColvoDesc* d) {
   P.ftiles_x = div_up(d->W, 32);
   P.ftiles_y = div_up(d->H, kFwdTileH);
   P.sm_blocks = div_up(d->W, kSmBW) * div_up(d->H, kSmBH);
+  for (int k = 0; k < d->S; ++k) {
+    const double lam = (double)d->smooth_weight / (double)(1 << k) / (double)d->S;
+    const double nx = (double)d->B * d->h[k] * (d->w[k] - 1), ny = (double)d->B * (d->h[k] - 1) * d->w[k];
+    P.sm_cx[k] = nx > 0 ? (float)(lam / nx) : 0.f;
+    P.sm_cy[k] = ny > 0 ? (float)(lam / ny) : 0.f;
+  }
 }
 
 size_t smooth_tiles(const ColvoDesc* d) { return (size_t)div_up(d->W, kSmBW) * div_up(d->H, kSmBH) * d->S; }

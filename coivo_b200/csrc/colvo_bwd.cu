@@ -66,6 +66,9 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_BWD)
   BwdConst (*cst)[kMaxS] = reinterpret_cast<BwdConst (*)[kMaxS]>(red + (kThreads / 32) * NS * 12);   // [NS][kMaxS]
   float (*pose_s)[12] = reinterpret_cast<float (*)[12]>(cst + NS);                                   // [NS]: R row-major, t
   float* cst_sm = reinterpret_cast<float*>(pose_s + NS);   // scale 0: 1/(mean+eps), sum(s d)/(n (mean+eps)^2)
+  // full[i]: the copies into coefficient buffer i have landed (cp.async arrivals); empty[i]: every thread is done reading it
+  unsigned long long* mbar = reinterpret_cast<unsigned long long*>(smem_raw + sizeof(float4) * 2 * kCN * 3 +
+                                                                   sizeof(double) * (kThreads / 32) * NS * 12 + 1024);
 
   pdl_trigger();         // the epilogue launch may become resident while this kernel drains
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
@@ -145,8 +148,14 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_BWD)
 #pragma unroll
       for (int ch = 0; ch < 3; ++ch) cp_async16(cbf + idx * 3 + ch, p + (long long)ch * P.HW, on);
     }
-    cp_async_commit();
+    mbar_arrive_cp_async(&mbar[k & 1]);      // this thread's share of full[k & 1]
   };
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) mbar_init(&mbar[i], kThreads);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();       // barriers initialised; per-frame constants visible
   stage_coef(0);
 
 #pragma unroll 1
@@ -157,11 +166,14 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_BWD)
 #pragma unroll
     for (int n = 0; n < NS; ++n) gt[n] = __ldg(geo_in + (long long)((b * P.N + n) * P.S + k) * P.HW + qo);
     const int own_sel = __ldg(sel + ((long long)b * P.S + k) * P.HW + qo);
-    cp_async_wait_all();
-#if !COLVO_EXP_NOBAR
-    __syncthreads();   // scale k landed for every thread (first pass: constants visible), nobody reads the other buffer
-#endif
-    if (k + 1 < P.S) stage_coef(k + 1);
+    // Two transaction barriers per buffer instead of a block barrier per scale: the copies of scale k+1 are issued
+    // once every thread has finished gathering from that buffer (scale k-1: a whole per-source phase ago), and the
+    // gather of scale k starts once the copies into its buffer have landed -- warps drift by up to one scale.
+    if (k + 1 < P.S) {
+      if (k >= 1) mbar_wait(&mbar[2 + ((k + 1) & 1)], ((k - 1) >> 1) & 1);     // empty[(k+1)&1]: gather(k-1) done everywhere
+      stage_coef(k + 1);
+    }
+    mbar_wait(&mbar[k & 1], (k >> 1) & 1);                                      // full[k&1]: scale k landed
     float dD = 0.f;
     // gather once per scale: every window centre has at most one winning source (texel .w = its index), so its
     // coefficients go to that source's accumulators (one pass over the 3x3 neighbourhood serves both sources;
@@ -194,6 +206,7 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_BWD)
         }
       }
     }
+    mbar_arrive(&mbar[2 + (k & 1)]);          // done reading coefficient buffer k & 1
     const float D_own = gt[0].w;
 #pragma unroll
     for (int n = 0; n < NS; ++n) {
@@ -439,7 +452,7 @@ static inline int div_up(int a, int b) { return (a + b - 1) / b; }
 template <int NS>
 static size_t photo_bwd_smem() {
   return sizeof(float4) * 2 * kCN * 3 + sizeof(double) * (kThreads / 32) * NS * 12 +
-         sizeof(BwdConst) * NS * kMaxS + sizeof(float) * NS * 12 + sizeof(float) * 2;
+         1024 /* per-frame constants, poses */ + 4 * sizeof(unsigned long long) /* mbarriers */;
 }
 
 cudaError_t launch_backward(const KP& P, const BwdBuffers& Wk, const float* grad_loss, const uint8_t* sel,

@@ -72,27 +72,36 @@ __global__ void __launch_bounds__(kThreads)
       dof += ((kSmBW >> k) + 2) * ((kSmBH >> k) + 2);
     }
   }
+  // (all tile loops below are 2-D -- warp = 32 consecutive columns, 8 rows per pass -- so no integer divisions)
+  const int tx = tid & 31, ty = tid >> 5;
   // ---- level 0: the full-resolution block + halo, and the inverse-depth tiles of every scale ----
   {
     const int hal = 1 << (P.S - 1), dw = kSmBW + 2 * hal, dh = kSmBH + 2 * hal, dn = dw * dh;
-    for (int idx = tid; idx < dn; idx += kThreads) {
-      const int r = idx / dw, c = idx - r * dw;
-      const int gy = Y0 - hal + r, gx = X0 - hal + c;
-      float v[3] = {0.f, 0.f, 0.f};
-      if (gy >= 0 && gy < P.H && gx >= 0 && gx < P.W) im.load3(gy * P.W + gx, v);
-      simg[idx] = v[0];
-      simg[dn + idx] = v[1];
-      simg[2 * dn + idx] = v[2];
+    for (int r = ty; r < dh; r += kThreads / 32) {
+      const int gy = Y0 - hal + r;
+      const bool row_in = gy >= 0 && gy < P.H;
+      for (int c = tx; c < dw; c += 32) {
+        const int gx = X0 - hal + c;
+        float v[3] = {0.f, 0.f, 0.f};
+        if (row_in && gx >= 0 && gx < P.W) im.load3(gy * P.W + gx, v);
+        const int idx = r * dw + c;
+        simg[idx] = v[0];
+        simg[dn + idx] = v[1];
+        simg[2 * dn + idx] = v[2];
+      }
     }
 #pragma unroll
     for (int k = 0; k < kMaxS; ++k) {
       if (k < P.S) {
-        const int hk = P.h[k], wk = P.w[k], dwk = (kSmBW >> k) + 2, dnk = dwk * ((kSmBH >> k) + 2);
+        const int hk = P.h[k], wk = P.w[k], dwk = (kSmBW >> k) + 2, dhk = (kSmBH >> k) + 2;
         const float* D = P.depth[k] + (long long)b * P.depth_bs[k];
-        for (int idx = tid; idx < dnk; idx += kThreads) {
-          const int r = idx / dwk, c = idx - r * dwk;
-          const int gy = (Y0 >> k) - 1 + r, gx = (X0 >> k) - 1 + c;
-          sdep[doff[k] + idx] = (gy >= 0 && gy < hk && gx >= 0 && gx < wk) ? f_rcp(__ldg(D + gy * wk + gx)) : 0.f;
+        for (int r = ty; r < dhk; r += kThreads / 32) {
+          const int gy = (Y0 >> k) - 1 + r;
+          const bool row_in = gy >= 0 && gy < hk;
+          for (int c = tx; c < dwk; c += 32) {
+            const int gx = (X0 >> k) - 1 + c;
+            sdep[doff[k] + r * dwk + c] = (row_in && gx >= 0 && gx < wk) ? f_rcp(__ldg(D + gy * wk + gx)) : 0.f;
+          }
         }
       }
     }
@@ -106,13 +115,14 @@ __global__ void __launch_bounds__(kThreads)
       const int pdw = (kSmBW >> (k - 1)) + 4 * hal, pdn = pdw * ((kSmBH >> (k - 1)) + 4 * hal);
       const float* src = simg + ioff[k - 1];
       float* dst = simg + ioff[k];
-      for (int idx = tid; idx < dn; idx += kThreads) {
-        const int r = idx / dw, c = idx - r * dw;
-        const int o = (2 * r) * pdw + 2 * c;
+      for (int r = ty; r < dh; r += kThreads / 32) {
+        for (int c = tx; c < dw; c += 32) {
+          const int o = (2 * r) * pdw + 2 * c, idx = r * dw + c;
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-          const float* q = src + ch * pdn + o;
-          dst[ch * dn + idx] = ((q[0] + q[1]) + (q[pdw] + q[pdw + 1])) * 0.25f;
+          for (int ch = 0; ch < 3; ++ch) {
+            const float* q = src + ch * pdn + o;
+            dst[ch * dn + idx] = ((q[0] + q[1]) + (q[pdw] + q[pdw + 1])) * 0.25f;
+          }
         }
       }
       __syncthreads();
@@ -128,12 +138,11 @@ __global__ void __launch_bounds__(kThreads)
     const float* I = simg + ioff[k];
     const float* Dr = sdep + doff[k];
     float* sf = O.sf[k] ? O.sf[k] + (long long)b * hk * wk : nullptr;
-    const double lam = (double)P.smooth_weight / (double)(1 << k) / (double)P.S;
-    const double nx = (double)P.B * hk * (wk - 1), ny = (double)P.B * (hk - 1) * wk;
-    const float cx = nx > 0 ? (float)(lam / nx) : 0.f, cy = ny > 0 ? (float)(lam / ny) : 0.f;
+    const float cx = P.sm_cx[k], cy = P.sm_cy[k];
     float acc[kSmVals] = {0.f, 0.f, 0.f, 0.f};      // at most 8 texels per thread and scale: fp32, then fp64 across threads
+    const int tw_log = 6 - k;                       // tw = kSmBW >> k is a power of two
     for (int i = tid; i < tw * th; i += kThreads) {
-      const int ly = i / tw, lx = i - ly * tw;
+      const int ly = i >> tw_log, lx = i & (tw - 1);
       const int gy = (Y0 >> k) + ly, gx = (X0 >> k) + lx;
       if (gy < hk && gx < wk) {
         const int o = (ly + hal) * dw + lx + hal, od = (ly + 1) * ddw + lx + 1;

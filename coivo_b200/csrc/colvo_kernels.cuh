@@ -38,6 +38,7 @@ struct KP {
   int h[kMaxS], w[kMaxS];
   float ry[kMaxS], rx[kMaxS];        // h_k / H, w_k / W rounded once to fp32 (oracle._upsample_axis)
   int sm_blocks;                     // k_smooth CTAs per image
+  float sm_cx[kMaxS], sm_cy[kMaxS];  // smoothness edge weights lambda_k / (S * #x-edges), lambda_k / (S * #y-edges)
   float alpha, c1, c2, eps_proj, eps_lcc, eps_disp, z_min, smooth_weight;
   unsigned flags;
   const void* tgt;                   // [B,3,H,W] fp32 planar, or [B,H,W,4] bf16 packed (COLVO_F_PACKED_BF16)
@@ -198,6 +199,27 @@ __device__ __forceinline__ float sample_plane(const float* __restrict__ plane, c
   d[2] = __ldg(plane + (r1 + t.x0));
   d[3] = __ldg(plane + (r1 + t.x1));
   return bilerp(d[0], d[1], d[2], d[3], t.wx, t.wy);
+}
+
+// ---- mbarrier (shared-memory transaction barrier) helpers: producers' cp.async completions arrive on it by
+// themselves, consumers poll a phase parity -- a block barrier with slack instead of a rendezvous ----
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+// all cp.async issued so far by this thread arrive on `bar` when they complete (counts as this thread's arrival)
+__device__ __forceinline__ void mbar_arrive_cp_async(unsigned long long* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("{\n .reg .b64 t;\n mbarrier.arrive.shared::cta.b64 t, [%0];\n}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n .reg .pred p;\n"
+      "W_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      " @p bra D_%=;\n bra W_%=;\n"
+      "D_%=:\n}\n" ::"r"(a), "r"(parity) : "memory");
 }
 
 // fire-and-forget float add to GLOBAL memory (RED.E.ADD.F32): explicit address space, so that a base pointer hidden
