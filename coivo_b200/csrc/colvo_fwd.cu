@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(kThreads)
   float* simg = reinterpret_cast<float*>(sm_raw);
   float* sdep = simg + sm_img_floats();
   double* red = reinterpret_cast<double*>(sdep + ((sm_dep_floats() + 1) & ~1));
+  pdl_trigger();
   const int tid = threadIdx.x, b = blockIdx.z;
   const int X0 = blockIdx.x * kSmBW, Y0 = blockIdx.y * kSmBH;
   const Img<PK> im = img_at<PK>(P, P.tgt, b * P.tgt_bf);
@@ -177,8 +178,9 @@ __global__ void __launch_bounds__(kThreads)
     block_reduce_store<kSmVals, double>(accd, red, O.part + ((long long)blk * P.S + k) * kSmVals);
     __syncthreads();          // red is reused by the next scale
   }
-  // launched programmatically behind k_photo_fwd, whose results it does not need: it fills that kernel's tail.
-  // k_finalize_fwd needs both, so this grid must not complete before its predecessor has.
+  // Launched programmatically behind k_warp_stats / k_lcc_solve, whose results it does not need: it fills the tail of
+  // that launch while k_photo_fwd (launched behind this one) runs its own input-only prologue.  k_photo_fwd waits
+  // on THIS grid, so this grid must not complete before its predecessors have.
   pdl_wait();
 }
 
@@ -408,25 +410,35 @@ __global__ void __launch_bounds__(kThreads)
       const double wg = (double)P.geo_weight / ((double)P.B * (double)P.N * (double)P.HW);
       for (int i = threadIdx.x; i < BNS * stat_chunks; i += kThreads) acc[1] += stat_part[(long long)i * kStatVals + 5] * wg;
     }
-    // smoothness: one warp per (b, k) sums the partials of that image's k_smooth CTAs, then applies
-    // 1 / (mean d + eps) (see k_smooth)
+    // smoothness: four lanes per (b, k) sum the partials of that image's k_smooth CTAs (64 pairs per pass of the
+    // block, fixed order), then 1 / (mean d + eps) is applied (see k_smooth)
     {
-      double sm_acc = 0.0;
-      for (int bk = wid; bk < P.B * P.S; bk += kThreads / 32) {
-        const int b = bk / P.S, k = bk - b * P.S;
+      const int grp = threadIdx.x >> 2, sub = threadIdx.x & 3;
+      for (int bk0 = 0; bk0 < P.B * P.S; bk0 += kThreads / 4) {
+        const int bk = bk0 + grp;
+        const bool on = bk < P.B * P.S;
+        const int b = on ? bk / P.S : 0, k = on ? bk - b * P.S : 0;
         const double* sp = smooth_part + ((long long)b * P.sm_blocks * P.S + k) * kSmVals;
         double sx = 0.0, sy = 0.0, sd = 0.0;
-        for (int t = lane; t < P.sm_blocks; t += 32) {
-          const double* q = sp + (long long)t * P.S * kSmVals;
-          sx += q[0];
-          sy += q[1];
-          sd += q[3];
+        if (on) {
+          for (int t = sub; t < P.sm_blocks; t += 4) {
+            const double* q = sp + (long long)t * P.S * kSmVals;
+            sx += q[0];
+            sy += q[1];
+            sd += q[3];
+          }
         }
-        sx = warp_sum(sx); sy = warp_sum(sy); sd = warp_sum(sd);
-        const double mean = sd / ((double)P.h[k] * (double)P.w[k]);
-        sm_acc += (sx * wk_s[k][0] + sy * wk_s[k][1]) / (mean + (double)P.eps_disp);
+#pragma unroll
+        for (int o = 1; o < 4; o <<= 1) {
+          sx += __shfl_xor_sync(0xffffffffu, sx, o);
+          sy += __shfl_xor_sync(0xffffffffu, sy, o);
+          sd += __shfl_xor_sync(0xffffffffu, sd, o);
+        }
+        if (on && sub == 0) {
+          const double mean = sd / ((double)P.h[k] * (double)P.w[k]);
+          acc[1] += (sx * wk_s[k][0] + sy * wk_s[k][1]) / (mean + (double)P.eps_disp);
+        }
       }
-      if (lane == 0) acc[1] += sm_acc;
     }
     for (int j = 0; j < 2; ++j) {
       double s = warp_sum(acc[j]);
@@ -579,18 +591,6 @@ cudaError_t launch_forward(const KP& P, const FwdBuffers& Wk, float* loss, float
   cudaError_t e = launch_pdl(k_lcc_solve, dim3(BNS), dim3(32), 0, st, P, Wk.stat_part, Wk.stat_chunks, ab,
                              save ? sv.frame : nullptr);
   if (e != cudaSuccess) return e;
-  dim3 grid(P.ftiles_x, P.ftiles_y, P.B);
-  {
-    ScopedKernelTimer tm(1, st);
-    float4* co = save ? reinterpret_cast<float4*>(sv.coef) : nullptr;
-    // opting in to > 48 KB of dynamic shared memory is a per-function, per-device attribute: cheap and idempotent
-    auto run = [&](auto kern, size_t smem) {
-      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      e = launch_pdl(kern, grid, dim3(kFwdThreads), smem, st, P, ab, sel, Wk.loss_part, Wk.g_part, need_g, co, Wk.iw);
-    };
-    if (P.N == 1) { if (pk) run(k_photo_fwd<1, true>, photo_fwd_smem<1>()); else run(k_photo_fwd<1, false>, photo_fwd_smem<1>()); }
-    else { if (pk) run(k_photo_fwd<2, true>, photo_fwd_smem<2>()); else run(k_photo_fwd<2, false>, photo_fwd_smem<2>()); }
-  }
   if (e != cudaSuccess) return e;
   {
     SmoothOut smo;
@@ -603,6 +603,19 @@ cudaError_t launch_forward(const KP& P, const FwdBuffers& Wk, float* loss, float
       e = launch_pdl(kern, g, dim3(kThreads), smem, st, P, smo);
     };
     if (pk) run(k_smooth<true>); else run(k_smooth<false>);
+  }
+  if (e != cudaSuccess) return e;
+  dim3 grid(P.ftiles_x, P.ftiles_y, P.B);
+  {
+    ScopedKernelTimer tm(1, st);
+    float4* co = save ? reinterpret_cast<float4*>(sv.coef) : nullptr;
+    // opting in to > 48 KB of dynamic shared memory is a per-function, per-device attribute: cheap and idempotent
+    auto run = [&](auto kern, size_t smem) {
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      e = launch_pdl(kern, grid, dim3(kFwdThreads), smem, st, P, ab, sel, Wk.loss_part, Wk.g_part, need_g, co, Wk.iw);
+    };
+    if (P.N == 1) { if (pk) run(k_photo_fwd<1, true>, photo_fwd_smem<1>()); else run(k_photo_fwd<1, false>, photo_fwd_smem<1>()); }
+    else { if (pk) run(k_photo_fwd<2, true>, photo_fwd_smem<2>()); else run(k_photo_fwd<2, false>, photo_fwd_smem<2>()); }
   }
   if (e != cudaSuccess) return e;
   const int nfin = 1 + (save ? BNS + P.B * P.S : 0);

@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(kFwdThreads, COLVO_MINB_FWD)
   }
   cp_async_commit();
   for (int i = tid; i < kFwdWarps * NV; i += kFwdThreads) sm.red[i] = 0.0;   // slots of unused scales stay 0
-  pdl_trigger();                // k_smooth (independent work) may fill this kernel's tail
+  pdl_trigger();
   cp_async_wait_all();          // the raw frames have landed
   __syncthreads();
 
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(kFwdThreads, COLVO_MINB_FWD)
   }
 
   // Everything above depends on the inputs only: launched programmatically, this CTA may have run it in the tail of
-  // k_warp_stats.  The warped frames and (a, b) are needed from here on.
+  // k_warp_stats / k_smooth.  The warped frames and (a, b) are needed from here on.
   pdl_wait();
   stage_scale(0, 1);
   float loss_acc = 0.f;
