@@ -229,3 +229,22 @@ def test_consistency_sweep_shapes_and_identity():
     assert abs(out[0, 1].item() - 1.25) < 1e-3 and abs(out[0, 2].item() + 0.0625) < 1e-3
     assert out[0, 0].item() < 1e-4 and out[1, 0].item() < 1e-4
     assert out[0, 3].item() > 0.9          # border rows/columns may round just outside
+
+
+def test_l1_kink_count_counts_winner_samples_on_the_kink():
+    """oracle.l1_kink_count (the L1 analogue of the arg-min near-tie protocol): identity pose, identical frames and
+    (a, b) = (1, 0) put every residual exactly on the kink; only samples of the WINNING source are counted."""
+    from coivo_b200.synthetic import make_triplets
+    d = make_triplets(1, 8, 12, N=2, S=1, seed=3)
+    tgt = d["tgt"]
+    srcs = torch.stack([tgt, tgt], dim=1)
+    pose = torch.eye(4).reshape(1, 1, 4, 4).repeat(1, 2, 1, 1)
+    ab = torch.tensor([1.0, 0.0]).reshape(1, 1, 1, 2).repeat(1, 2, 1, 1)
+    sel = torch.full((1, 1, 8, 12), 2, dtype=torch.uint8)              # source 0 wins everywhere
+    n = O.l1_kink_count(d["depth"], pose, d["K"], tgt, srcs, sel, ab)
+    assert 0.95 * 3 * 8 * 12 <= n <= 3 * 8 * 12          # (the identity warp is exact up to the last ulp of u', v')
+    sel[:, :, :4] = 0                                                   # an identity candidate wins the top half
+    n_half = O.l1_kink_count(d["depth"], pose, d["K"], tgt, srcs, sel, ab)
+    assert 0.95 * 3 * 4 * 12 <= n_half <= 3 * 4 * 12
+    ab2 = ab.clone(); ab2[..., 1] = 0.25                                # off the kink
+    assert O.l1_kink_count(d["depth"], pose, d["K"], tgt, srcs, sel, ab2) == 0
