@@ -12,6 +12,9 @@
 //   k_pose_final     deterministic reduction of the pose-gradient partials
 #include "colvo_kernels.cuh"
 
+#ifndef COLVO_BWD_PIPE       // 1: software pipeline of the per-scale loads: the saved projection of scale k+1 is fetched during
+#define COLVO_BWD_PIPE 0     //    scale k, and the taps of scale k are issued BEFORE its coefficient gather (more registers)
+#endif
 #ifndef COLVO_EXP_NOBAR      // timing experiments only (wrong results)
 #define COLVO_EXP_NOBAR 0
 #endif
@@ -158,14 +161,41 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_BWD)
   __syncthreads();       // barriers initialised; per-frame constants visible
   stage_coef(0);
 
+#if COLVO_BWD_PIPE
+  float4 gt_next[NS];
+#pragma unroll
+  for (int n = 0; n < NS; ++n) gt_next[n] = __ldg(geo_in + (long long)((b * P.N + n) * P.S) * P.HW + qo);
+  int sel_next = __ldg(sel + ((long long)b * P.S) * P.HW + qo);
+#endif
 #pragma unroll 1
   for (int k = 0; k < P.S; ++k) {
     const float4* cb = coef[k & 1];
     // projection of the own pixel into both sources, and which candidate won here
     float4 gt[NS];
+#if COLVO_BWD_PIPE
+#pragma unroll
+    for (int n = 0; n < NS; ++n) gt[n] = gt_next[n];
+    const int own_sel = sel_next;
+    if (k + 1 < P.S) {
+#pragma unroll
+      for (int n = 0; n < NS; ++n) gt_next[n] = __ldg(geo_in + (long long)((b * P.N + n) * P.S + k + 1) * P.HW + qo);
+      sel_next = __ldg(sel + ((long long)b * P.S + k + 1) * P.HW + qo);
+    }
+    // taps and texels of both sources now, so that their latency hides behind the coefficient gather
+    Taps tp[NS];
+    Texels tq[NS];
+#pragma unroll
+    for (int n = 0; n < NS; ++n) {
+      const Img<PK> src = img_at<PK>(P, P.srcs, b * P.src_bf + n * P.src_nf);
+      tp[n] = make_taps(gt[n].x, gt[n].y, P.W, P.H);
+      const int r0 = tp[n].y0 * P.W, r1 = tp[n].y1 * P.W;
+      src.load_taps(r0 + tp[n].x0, r0 + tp[n].x1, r1 + tp[n].x0, r1 + tp[n].x1, tq[n]);
+    }
+#else
 #pragma unroll
     for (int n = 0; n < NS; ++n) gt[n] = __ldg(geo_in + (long long)((b * P.N + n) * P.S + k) * P.HW + qo);
     const int own_sel = __ldg(sel + ((long long)b * P.S + k) * P.HW + qo);
+#endif
     // Two transaction barriers per buffer instead of a block barrier per scale: the copies of scale k+1 are issued
     // once every thread has finished gathering from that buffer (scale k-1: a whole per-source phase ago), and the
     // gather of scale k starts once the copies into its buffer have landed -- warps drift by up to one scale.
@@ -221,10 +251,16 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_BWD)
         Geo g;
         g.u = gt[n].x; g.v = gt[n].y; g.iz = gt[n].z; g.rx = own_rx; g.ry = own_ry;
         g.valid = (__float_as_uint(gt[n].w) & 1u) != 0u;
+#if COLVO_BWD_PIPE
+        const Taps t = tp[n];
+        const Texels& tx4 = tq[n];
+        const int r0 = t.y0 * P.W, r1 = t.y1 * P.W;
+#else
         const Taps t = make_taps(g.u, g.v, P.W, P.H);
         Texels tx4;
         const int r0 = t.y0 * P.W, r1 = t.y1 * P.W;
         src.load_taps(r0 + t.x0, r0 + t.x1, r1 + t.x0, r1 + t.x1, tx4);
+#endif
         const float wl1 = (own_sel == NS + n) ? c.wl1 : 0.f;
         float du = 0.f, dv = 0.f, hq[3];
 #pragma unroll

@@ -19,7 +19,7 @@ constexpr int kFwdThreads = kFwdWarps * 32;
 constexpr int kFwdTileH = kFwdWarps * kFwdRows;   // 16
 constexpr int kStatPPT = 8;      // pixels per thread in the LCC statistics pass
 constexpr int kStatVals = 6;     // per (frame, chunk): n, Sx, Sy, Sxx, Sxy, sum of geometric-consistency diffs
-constexpr int kSmBW = 64, kSmBH = 32; // full-resolution pixels per smoothness block (k_smooth)
+constexpr int kSmBW = 64, kSmBH = 16; // full-resolution pixels per smoothness block (k_smooth)
 constexpr int kSmVals = 4;            // per block and scale: sum over x edges, sum over y edges, sum s*d, sum d
 
 // saved[] layout: doubles  [B*N*S][kSavedPerFrame]  n, mean_x, mean_y, 1/(n (var+eps)), a, b, G_a, G_b

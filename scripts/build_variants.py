@@ -5,10 +5,9 @@ from coivo_b200 import _lib
 
 VARIANTS = {
     "base": [],
-    "nobar": ["COLVO_EXP_NOBAR=1"],
-    "nogather": ["COLVO_EXP_NOGATHER=1"],
-    "nored": ["COLVO_EXP_NORED=1"],
-    "noall": ["COLVO_EXP_NORED=1", "COLVO_EXP_NOGATHER=1", "COLVO_EXP_NOBAR=1"],
+    "pipe2": ["COLVO_BWD_PIPE=1", "COLVO_MINB_BWD=2"],
+    "pipe3": ["COLVO_BWD_PIPE=1", "COLVO_MINB_BWD=3"],
+    "b2": ["COLVO_MINB_BWD=2"],
 }
 out = os.path.join(os.path.dirname(_lib.PKG_DIR), "build", "variants")
 os.makedirs(out, exist_ok=True)
