@@ -429,13 +429,45 @@ __global__ void __launch_bounds__(kThreads)
   const int hk = P.h[k], wk = P.w[k], n = hk * wk;
   const int G = 1 << (k - 1), L = G * G;            // lanes per texel
   const int gid = blockIdx.x * kThreads + threadIdx.x;
-  const int idx = gid / L, sub = gid - idx * L;
+  const int idx = gid >> (2 * (k - 1)), sub = gid & (L - 1);
   const bool active = idx < n;
   const int i = active ? idx / wk : 0, j = active ? idx - (idx / wk) * wk : 0;
   const float* dD = ((k == 1) ? dD1 : (k == 2 ? dD2 : dD3)) + (long long)b * P.HW;
   const float ry = P.ry[k], rx = P.rx[k];
   float acc = 0.f;
-  if (active) {
+  const int f = 1 << k;
+  if ((hk << k) == P.H && (wk << k) == P.W) {
+    // Exact 2^k ratio (the usual case): pixel v contributes to texel i with the triangle weight
+    // 1 - |(v + 0.5) / f - 0.5 - i| -- every operation of the pinned up-sample is exact in fp32 here, so this is bit-for-bit
+    // the forward's weight -- except inside the clamped half-texel borders, which put their whole weight on the border
+    // texel.  The 2f x 2f footprint splits into 4 x 4 sub-blocks, one per lane: 16 loads and FMAs, no axis evaluation.
+    if (active) {
+      const int half = f >> 1, sr = sub >> (k - 1), sc = sub & (G - 1);
+      const float inv_f = 1.0f / (float)f;
+      const int vb = f * i - half + 4 * sr, ub = f * j - half + 4 * sc;
+      float wx[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int u = ub + c;
+        float w = 1.0f - fabsf(((float)(4 * sc + c) + 0.5f) * inv_f - 1.0f);
+        if ((j == 0 && u < half) || (j == wk - 1 && u >= f * (wk - 1) + half)) w = 1.0f;
+        wx[c] = (u >= 0 && u < P.W) ? w : 0.f;
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int v = vb + r;
+        float w = 1.0f - fabsf(((float)(4 * sr + r) + 0.5f) * inv_f - 1.0f);
+        if ((i == 0 && v < half) || (i == hk - 1 && v >= f * (hk - 1) + half)) w = 1.0f;
+        if (v >= 0 && v < P.H) {
+          const float* rowp = dD + v * P.W;
+          float row = 0.f;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) row = fmaf(wx[c], __ldg(rowp + imin(imax(ub + c, 0), P.W - 1)), row);
+          acc = fmaf(w, row, acc);
+        }
+      }
+    }
+  } else if (active) {
     // full-res rows v with source coordinate in (i-1, i+1): conservative bounds, exact test inside
     int v_lo = imax(0, (int)floorf(((float)i - 0.5f) / ry - 0.5f) - 1);
     int v_hi = imin(P.H - 1, (int)ceilf(((float)i + 1.5f) / ry - 0.5f) + 1);
