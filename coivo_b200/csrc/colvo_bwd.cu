@@ -161,6 +161,9 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_BWD)
   __syncthreads();       // barriers initialised; per-frame constants visible
   stage_coef(0);
 
+  // Everything above reads only what the forward saved.  Launched programmatically behind k_zero, the scatter targets
+  // are guaranteed to be zero from here on.
+  pdl_wait();
 #if COLVO_BWD_PIPE
   float4 gt_next[NS];
 #pragma unroll
@@ -517,6 +520,16 @@ __global__ void __launch_bounds__(kThreads)
 // ------------------------------------------------------------------------------------------
 static inline int div_up(int a, int b) { return (a + b - 1) / b; }
 
+// Zero-fill of the scatter targets as a kernel (not a memset node), so that k_photo_bwd can be launched
+// programmatically behind it and run its prologue (constants, barriers, first coefficient tile) meanwhile.
+__global__ void __launch_bounds__(kThreads) k_zero(float4* __restrict__ a, long long na, float4* __restrict__ b, long long nb) {
+  pdl_trigger();
+  const long long stride = (long long)gridDim.x * kThreads;
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < na; i += stride) a[i] = z;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < nb; i += stride) b[i] = z;
+}
+
 template <int NS>
 static size_t photo_bwd_smem() {
   return sizeof(float4) * 2 * kCN * 3 + sizeof(double) * (kThreads / 32) * NS * 12 +
@@ -526,14 +539,17 @@ static size_t photo_bwd_smem() {
 cudaError_t launch_backward(const KP& P, const BwdBuffers& Wk, const float* grad_loss, const uint8_t* sel,
                             const SavedView& sv, float* const* grad_depth, float* grad_T, float* grad_srcs,
                             float* grad_src_depth, cudaStream_t st) {
-  cudaError_t e;
-  if (grad_src_depth) {
+  cudaError_t e = cudaSuccess;
+  const bool zero_sd = grad_src_depth != nullptr && (P.HW % 4 == 0) && (((uintptr_t)grad_src_depth & 15u) == 0);
+  if (grad_src_depth && !zero_sd) {      // odd sizes / alignment: plain memset
     e = cudaMemsetAsync(grad_src_depth, 0, sizeof(float) * (size_t)P.B * P.N * P.HW, st);
     if (e != cudaSuccess) return e;
   }
-  if (grad_srcs) {
-    e = cudaMemsetAsync(Wk.gsrc4, 0, sizeof(float4) * (size_t)P.B * P.N * P.HW, st);
-    if (e != cudaSuccess) return e;
+  const bool zeroed = grad_srcs || zero_sd;
+  if (zeroed) {
+    const long long na = grad_srcs ? (long long)P.B * P.N * P.HW : 0;
+    const long long nb = zero_sd ? (long long)P.B * P.N * P.HW / 4 : 0;
+    k_zero<<<148 * 4, kThreads, 0, st>>>(Wk.gsrc4, na, reinterpret_cast<float4*>(grad_src_depth), nb);
   }
   dim3 grid(P.tiles_x, P.tiles_y, P.B);
   {
@@ -541,9 +557,14 @@ cudaError_t launch_backward(const KP& P, const BwdBuffers& Wk, const float* grad
     // opting in to > 48 KB of dynamic shared memory is a per-function, per-device attribute: cheap and idempotent
     auto launch = [&](auto kern, size_t smem) {
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      kern<<<grid, kThreads, smem, st>>>(P, grad_loss, sel, sv.frame, sv.scale, sv.s_field[0], sv.coef, sv.geo, grad_depth[0],
-                                         Wk.dDhat[1], Wk.dDhat[2], Wk.dDhat[3], grad_srcs ? Wk.gsrc4 : nullptr, grad_src_depth,
-                                         Wk.pose_part);
+      if (zeroed)
+        e = launch_pdl(kern, grid, dim3(kThreads), smem, st, P, grad_loss, sel, (const double*)sv.frame, (const double*)sv.scale,
+                       (const float*)sv.s_field[0], (const float*)sv.coef, (const float4*)sv.geo, grad_depth[0], Wk.dDhat[1],
+                       Wk.dDhat[2], Wk.dDhat[3], grad_srcs ? Wk.gsrc4 : nullptr, grad_src_depth, Wk.pose_part);
+      else
+        kern<<<grid, kThreads, smem, st>>>(P, grad_loss, sel, sv.frame, sv.scale, sv.s_field[0], sv.coef, sv.geo, grad_depth[0],
+                                           Wk.dDhat[1], Wk.dDhat[2], Wk.dDhat[3], grad_srcs ? Wk.gsrc4 : nullptr, grad_src_depth,
+                                           Wk.pose_part);
     };
     const bool geo = P.src_depth != nullptr, pk = (P.flags & 16u) != 0;
     if (P.N == 1) {

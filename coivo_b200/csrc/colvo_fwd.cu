@@ -387,6 +387,7 @@ __global__ void __launch_bounds__(kThreads)
                    int need_g) {
   __shared__ double sm[(kThreads / 32) * 2];
   __shared__ double wk_s[kMaxS][2];
+  pdl_wait();                                   // launched programmatically behind k_photo_fwd
   const int tiles = P.ftiles_x * P.ftiles_y;    // k_photo_fwd's tiling
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int BNS = P.B * P.N * P.S;
@@ -619,8 +620,9 @@ cudaError_t launch_forward(const KP& P, const FwdBuffers& Wk, float* loss, float
   }
   if (e != cudaSuccess) return e;
   const int nfin = 1 + (save ? BNS + P.B * P.S : 0);
-  k_finalize_fwd<<<nfin, kThreads, 0, st>>>(P, Wk.loss_part, Wk.g_part, Wk.smooth_part, Wk.stat_part, Wk.stat_chunks,
-                                            loss, sv.frame, sv.scale, need_g);
+  e = launch_pdl(k_finalize_fwd, dim3(nfin), dim3(kThreads), 0, st, P, (const double*)Wk.loss_part, (const double*)Wk.g_part,
+                 (const double*)Wk.smooth_part, (const double*)Wk.stat_part, Wk.stat_chunks, loss, sv.frame, sv.scale, need_g);
+  if (e != cudaSuccess) return e;
   return cudaGetLastError();
 }
 
