@@ -116,8 +116,8 @@ EXPORTS = tuple(_SIGS)
 
 K_PHOTO_FWD, K_PHOTO_BWD, K_WARP_STATS = 1, 2, 3
 # kernels launched by one forward + one backward (S > 1, LCC on); bench.py's gpu_launches
-KERNELS_FWD = ("k_warp_stats", "k_lcc_solve", "k_photo_fwd", "k_smooth", "k_finalize_fwd")
-KERNELS_BWD = ("k_photo_bwd", "k_depth_gather")      # (k_depth_gather's launch carries the pose reduction and the unpack)
+KERNELS_FWD = ("k_warp_stats", "k_lcc_solve", "k_smooth", "k_photo_fwd", "k_smooth", "k_finalize_fwd")   # (k_smooth: two half-batch launches)
+KERNELS_BWD = ("k_zero", "k_photo_bwd", "k_depth_gather")   # (k_depth_gather's launch carries the pose reduction and the unpack)
 
 
 def load(auto_build: bool = True) -> ctypes.CDLL:

@@ -51,13 +51,13 @@ __host__ __device__ constexpr int sm_dep_floats() {   // inverse-depth tiles of 
 
 template <bool PK>
 __global__ void __launch_bounds__(kThreads)
-    k_smooth(KP P, SmoothOut O) {
+    k_smooth(KP P, SmoothOut O, int b0) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
   float* simg = reinterpret_cast<float*>(sm_raw);
   float* sdep = simg + sm_img_floats();
   double* red = reinterpret_cast<double*>(sdep + ((sm_dep_floats() + 1) & ~1));
   pdl_trigger();
-  const int tid = threadIdx.x, b = blockIdx.z;
+  const int tid = threadIdx.x, b = b0 + blockIdx.z;
   const int X0 = blockIdx.x * kSmBW, Y0 = blockIdx.y * kSmBH;
   const Img<PK> im = img_at<PK>(P, P.tgt, b * P.tgt_bf);
 
@@ -593,18 +593,23 @@ cudaError_t launch_forward(const KP& P, const FwdBuffers& Wk, float* loss, float
                              save ? sv.frame : nullptr);
   if (e != cudaSuccess) return e;
   if (e != cudaSuccess) return e;
-  {
-    SmoothOut smo;
-    smo.part = Wk.smooth_part;
-    for (int k = 0; k < kMaxS; ++k) smo.sf[k] = save ? sv.s_field[k] : nullptr;
-    const size_t smem = sizeof(float) * (sm_img_floats() + ((sm_dep_floats() + 1) & ~1)) + sizeof(double) * (kThreads / 32) * kSmVals;
-    dim3 g(div_up(P.W, kSmBW), div_up(P.H, kSmBH), P.B);
+  // The smoothness pass depends on the inputs only; it is launched in two halves of the batch, one behind the
+  // statistics pass and one behind the tile kernel, so that each fills the tail of a big launch.
+  SmoothOut smo;
+  smo.part = Wk.smooth_part;
+  for (int k = 0; k < kMaxS; ++k) smo.sf[k] = save ? sv.s_field[k] : nullptr;
+  const size_t sm_smem = sizeof(float) * (sm_img_floats() + ((sm_dep_floats() + 1) & ~1)) + sizeof(double) * (kThreads / 32) * kSmVals;
+  auto run_smooth = [&](int b0, int nb) {
+    if (nb <= 0) return;
+    dim3 g(div_up(P.W, kSmBW), div_up(P.H, kSmBH), nb);
     auto run = [&](auto kern) {
-      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      e = launch_pdl(kern, g, dim3(kThreads), smem, st, P, smo);
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_smem);
+      e = launch_pdl(kern, g, dim3(kThreads), sm_smem, st, P, smo, b0);
     };
     if (pk) run(k_smooth<true>); else run(k_smooth<false>);
-  }
+  };
+  const int b_first = (P.B + 1) / 2;
+  run_smooth(0, b_first);
   if (e != cudaSuccess) return e;
   dim3 grid(P.ftiles_x, P.ftiles_y, P.B);
   {
@@ -618,6 +623,8 @@ cudaError_t launch_forward(const KP& P, const FwdBuffers& Wk, float* loss, float
     if (P.N == 1) { if (pk) run(k_photo_fwd<1, true>, photo_fwd_smem<1>()); else run(k_photo_fwd<1, false>, photo_fwd_smem<1>()); }
     else { if (pk) run(k_photo_fwd<2, true>, photo_fwd_smem<2>()); else run(k_photo_fwd<2, false>, photo_fwd_smem<2>()); }
   }
+  if (e != cudaSuccess) return e;
+  run_smooth(b_first, P.B - b_first);
   if (e != cudaSuccess) return e;
   const int nfin = 1 + (save ? BNS + P.B * P.S : 0);
   e = launch_pdl(k_finalize_fwd, dim3(nfin), dim3(kThreads), 0, st, P, (const double*)Wk.loss_part, (const double*)Wk.g_part,
