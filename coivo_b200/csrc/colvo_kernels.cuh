@@ -185,6 +185,13 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool pr
   const int sz = pred ? 16 : 0;
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(sz));
 }
+// the same with the 32-bit shared-window address already at hand (hoisted out of an unrolled staging loop)
+__device__ __forceinline__ void cp_async16_s(unsigned saddr, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async4_s(unsigned saddr, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(saddr), "l"(gmem));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 template <int N>

@@ -27,7 +27,13 @@ CV_HD float p_mul(float a, float b) { return __fmul_rn(a, b); }
 CV_HD float p_div(float a, float b) { return __fdiv_rn(a, b); }
 CV_HD float p_rcp(float a) { return __frcp_rn(a); }
 CV_HD float f_fma(float a, float b, float c) { return fmaf(a, b, c); }
-CV_HD float f_rcp(float a) { return __fdividef(1.0f, a); }   // approximate (MUFU.RCP): SSIM only, never the pinned chain
+// approximate reciprocal, one MUFU.RCP (rel. error 2^-23; __fdividef(1, a) wraps it in four range-fix-up
+// instructions that the SSIM denominators, >= 9e-8, never need): SSIM and 1/D only, never the pinned chain
+CV_HD float f_rcp(float a) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+  return r;
+}
 #else
 // host build: compiled with -ffp-contract=off, so each operator rounds once
 CV_HD float p_add(float a, float b) { volatile float r = a + b; return r; }
@@ -163,6 +169,8 @@ CV_HD SsimParts ssim_parts(float mut, float st, float stxy, float muy, float sy,
 }
 CV_HD float clamp01(float t) { return fminf(fmaxf(t, 0.f), 1.f); }
 CV_HD float sgn(float x) { return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f); }
+// w * sgn(x) with sgn(0) = 0 (torch's sub-gradient of |.|): copysign + one select instead of two compares and a convert
+CV_HD float sgn_scaled(float w, float x) { return (x != 0.f) ? copysignf(w, x) * 1.0f : 0.f; }
 
 // coefficient fields of the SSIM adjoint in gather form (re-derived for
 // raw moments):  d pe_p / d x_q  =  ca_p + x_q * cb_p + y_q * cg_p   for every occurrence of q in

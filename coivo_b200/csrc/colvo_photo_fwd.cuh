@@ -79,51 +79,71 @@ __device__ __forceinline__ void row_sums(RowH<NS>& R, RowY& Y, const float4* __r
 // the target side of one window
 struct WinY {
   float muy[3], sgy[3], yc[3];
+  float sy9[3], muy2[3], k1[3], k2[3];     // 9 mu_y, 2 mu_y, mu_y^2 + C1, var_y + C2: shared by every candidate of the window
 };
+__device__ __forceinline__ void winy_derive(WinY& y, float c1, float c2) {
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    y.sy9[c] = 9.0f * y.muy[c];
+    y.muy2[c] = y.muy[c] + y.muy[c];
+    y.k1[c] = fmaf(y.muy[c], y.muy[c], c1);
+    y.k2[c] = y.sgy[c] + c2;
+  }
+}
+// per-candidate constants of the calibration (a, b)
+struct CalK {
+  float a, b, a2_9, ta_9, ta;              // a^2 / 9 and 2a / 9 act on the 9x-scaled window moments
+};
+__device__ __forceinline__ CalK make_calk(float a, float b) {
+  CalK k;
+  k.a = a; k.b = b; k.a2_9 = a * a * (1.0f / 9.0f); k.ta = 2.f * a; k.ta_9 = k.ta * (1.0f / 9.0f);
+  return k;
+}
 
-// photometric error of one candidate from its 3x3 window SUMS (value only)
+// photometric error of one candidate from its 3x3 window SUMS (value only), times 3
 //   pe = alpha * mean_c clamp((1 - SSIM_c)/2) + (1 - alpha) * mean_c |a x_c + b - y_c|
-__device__ __forceinline__ float pe_value(const float (&Sx)[3], const float (&Sxx)[3], const float (&Sxy)[3],
-                                          const float (&xc)[3], const WinY& y, float a, float b, float alpha, float c1,
-                                          float c2) {
-  const float i9 = 1.0f / 9.0f, a2 = a * a, ta = 2.f * a;
+// The window moments stay scaled by 9 (s9 = 9 var_x, sxy9 = 9 cov_xy): the factor rides on a^2/9 and 2a/9.
+__device__ __forceinline__ float pe_value3(const float (&Sx)[3], const float (&Sxx)[3], const float (&Sxy)[3],
+                                           const float (&xc)[3], const WinY& y, const CalK& k, float alpha, float c1,
+                                           float c2) {
   float pe = 0.f;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    const float mu = Sx[c] * i9;
-    const float s = fmaf(-mu, mu, Sxx[c] * i9);
-    const float sxy = fmaf(-mu, y.muy[c], Sxy[c] * i9);
-    const float mut = fmaf(a, mu, b);
-    const float A1 = fmaf(2.f * mut, y.muy[c], c1);
-    const float A2 = fmaf(ta, sxy, c2);
-    const float B1 = fmaf(mut, mut, fmaf(y.muy[c], y.muy[c], c1));
-    const float B2 = fmaf(a2, s, y.sgy[c] + c2);
+    const float mu = Sx[c] * (1.0f / 9.0f);
+    const float s9 = fmaf(-mu, Sx[c], Sxx[c]);
+    const float sxy9 = fmaf(-mu, y.sy9[c], Sxy[c]);
+    const float mut = fmaf(k.a, mu, k.b);
+    const float A1 = fmaf(mut, y.muy2[c], c1);
+    const float A2 = fmaf(k.ta_9, sxy9, c2);
+    const float B1 = fmaf(mut, mut, y.k1[c]);
+    const float B2 = fmaf(k.a2_9, s9, y.k2[c]);
     const float S = A1 * A2 * f_rcp(B1 * B2);
     const float t = __saturatef(fmaf(-0.5f, S, 0.5f));
-    const float diff = fmaf(a, xc[c], b) - y.yc[c];
+    const float diff = fmaf(k.a, xc[c], k.b) - y.yc[c];
     pe = fmaf(alpha, t, pe);
     pe = fmaf(1.f - alpha, fabsf(diff), pe);
   }
-  return pe * (1.0f / 3.0f);
+  return pe;
 }
 
 // adjoint pieces of the winning candidate: unit-weight SSIM adjoint coefficients (ca, cb, cg) per channel
 // (colvo_math.cuh::coef_from_parts) and the terms of d pe / d a, d pe / d b
 __device__ __forceinline__ void pe_adjoint(const float (&Sx)[3], const float (&Sxx)[3], const float (&Sxy)[3],
-                                           const float (&xc)[3], const WinY& y, float a, float b, float alpha, float c1,
+                                           const float (&xc)[3], const WinY& y, const CalK& k, float alpha, float c1,
                                            float c2, float (&ca)[3], float (&cb)[3], float (&cg)[3], float& dpa,
                                            float& dpb) {
-  const float i9 = 1.0f / 9.0f, a2 = a * a, ta = 2.f * a;
+  const float a = k.a, a2 = a * a;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    const float mu = Sx[c] * i9;
-    const float s = fmaf(-mu, mu, Sxx[c] * i9);
-    const float sxy = fmaf(-mu, y.muy[c], Sxy[c] * i9);
-    const float mut = fmaf(a, mu, b);
-    const float A1 = fmaf(2.f * mut, y.muy[c], c1);
-    const float A2 = fmaf(ta, sxy, c2);
-    const float B1 = fmaf(mut, mut, fmaf(y.muy[c], y.muy[c], c1));
-    const float B2 = fmaf(a2, s, y.sgy[c] + c2);
+    const float mu = Sx[c] * (1.0f / 9.0f);
+    const float s9 = fmaf(-mu, Sx[c], Sxx[c]);
+    const float sxy9 = fmaf(-mu, y.sy9[c], Sxy[c]);
+    const float s = s9 * (1.0f / 9.0f), sxy = sxy9 * (1.0f / 9.0f);
+    const float mut = fmaf(a, mu, k.b);
+    const float A1 = fmaf(mut, y.muy2[c], c1);
+    const float A2 = fmaf(k.ta_9, sxy9, c2);
+    const float B1 = fmaf(mut, mut, y.k1[c]);
+    const float B2 = fmaf(k.a2_9, s9, y.k2[c]);
     const float iB = f_rcp(B1 * B2);
     const float iB1 = iB * B2, iB2 = iB * B1;
     const float r2 = A2 * iB2;
@@ -133,10 +153,10 @@ __device__ __forceinline__ void pe_adjoint(const float (&Sx)[3], const float (&S
     const float dmu = 2.f * iB1 * fmaf(y.muy[c], r2, -S * mut);
     const float dsx = -S * iB2;
     const float dsxy = 2.f * A1 * iB;
-    const float diff = fmaf(a, xc[c], b) - y.yc[c];
-    const float sg = (1.f - alpha) * sgn(diff);
+    const float diff = fmaf(a, xc[c], k.b) - y.yc[c];
+    const float sg = sgn_scaled(1.f - alpha, diff);
     const float act = in01 ? -0.5f * alpha : 0.f;
-    dpa += fmaf(act, fmaf(dmu, mu, fmaf(dsx * ta, s, dsxy * sxy)), sg * xc[c]);
+    dpa += fmaf(act, fmaf(dmu, mu, fmaf(dsx * k.ta, s, dsxy * sxy)), sg * xc[c]);
     dpb += fmaf(act, dmu, sg);
     const float actc = act * (1.0f / 27.0f);
     const float d1 = a * dmu, d2 = a2 * dsx, d3 = a * dsxy;
@@ -170,10 +190,14 @@ __global__ void __launch_bounds__(kFwdThreads, COLVO_MINB_FWD)
   auto stage_scale = [&](int k, int buf) {      // warped frames of scale k -> sm.x[buf]
 #pragma unroll
     for (int n = 0; n < NS; ++n) {
+      // frame base hidden from the optimiser + 32-bit offsets: one IMAD.WIDE per copy (see Img<false>::load_taps);
+      // the shared-window address is formed once, the rounds are immediate offsets
       const float4* src = iw + (long long)((b * P.N + n) * P.S + k) * P.HW;
+      asm volatile("" : "+l"(src));
+      const unsigned sa = (unsigned)__cvta_generic_to_shared(&sm.x[buf][n][tid]);
 #pragma unroll
       for (int j = 0; j < kStageRounds; ++j)
-        if (goff[j] >= 0) cp_async16(&sm.x[buf][n][tid + j * kFwdThreads], src + goff[j], true);
+        if (goff[j] >= 0) cp_async16_s(sa + j * kFwdThreads * (unsigned)sizeof(float4), src + (unsigned)goff[j]);
     }
     cp_async_commit();
   };
@@ -182,25 +206,22 @@ __global__ void __launch_bounds__(kFwdThreads, COLVO_MINB_FWD)
   // 4-byte cp.async straight into the texel components, so all 9 loads per position are in flight at once;
   // packed bf16 is widened on the way in (all loads first, then the stores).
   if constexpr (!PK) {
-    const float* tg = static_cast<const float*>(P.tgt) + (long long)b * P.tgt_bf * P.frame_el;
-#pragma unroll
-    for (int j = 0; j < kStageRounds; ++j)
-      if (goff[j] >= 0) {
-        float* dst = reinterpret_cast<float*>(&sm.y[tid + j * kFwdThreads]);
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) cp_async4(dst + ch, tg + (ch * P.HW + goff[j]), true);
-      }
-#pragma unroll
-    for (int n = 0; n < NS; ++n) {
-      const float* sp = static_cast<const float*>(P.srcs) + (long long)(b * P.src_bf + n * P.src_nf) * P.frame_el;
+    const unsigned hw = P.HW;
+    auto stage_planar = [&](const float* fb, float4* dst0) {
+      asm volatile("" : "+l"(fb));
+      const unsigned sa = (unsigned)__cvta_generic_to_shared(dst0 + tid);
 #pragma unroll
       for (int j = 0; j < kStageRounds; ++j)
         if (goff[j] >= 0) {
-          float* dst = reinterpret_cast<float*>(&sm.x[0][n][tid + j * kFwdThreads]);
 #pragma unroll
-          for (int ch = 0; ch < 3; ++ch) cp_async4(dst + ch, sp + (ch * P.HW + goff[j]), true);
+          for (int ch = 0; ch < 3; ++ch)
+            cp_async4_s(sa + (j * kFwdThreads * 4 + ch) * (unsigned)sizeof(float), fb + ((unsigned)goff[j] + ch * hw));
         }
-    }
+    };
+    stage_planar(static_cast<const float*>(P.tgt) + (long long)b * P.tgt_bf * P.frame_el, sm.y);
+#pragma unroll
+    for (int n = 0; n < NS; ++n)
+      stage_planar(static_cast<const float*>(P.srcs) + (long long)(b * P.src_bf + n * P.src_nf) * P.frame_el, sm.x[0][n]);
   } else {
     uint2 raw[1 + NS][kStageRounds];
 #pragma unroll
@@ -258,11 +279,14 @@ __global__ void __launch_bounds__(kFwdThreads, COLVO_MINB_FWD)
             Sxy[n][c] = R[0].sxy[n][c] + R[1].sxy[n][c] + R[2].sxy[n][c];
           }
         }
-        float best = pe_value(Sx[0], Sxx[0], Sxy[0], R[(j - 1) % 3].xc[0], wy, 1.0f, 0.0f, alpha, c1, c2);
+        winy_derive(wy, c1, c2);
+        const CalK kid = make_calk(1.0f, 0.0f);
+        // (candidates are compared as 3 * pe: the mean over channels is a common factor)
+        float best = pe_value3(Sx[0], Sxx[0], Sxy[0], R[(j - 1) % 3].xc[0], wy, kid, alpha, c1, c2);
         int sel = 0;
 #pragma unroll
         for (int n = 1; n < NS; ++n) {
-          const float pe = pe_value(Sx[n], Sxx[n], Sxy[n], R[(j - 1) % 3].xc[n], wy, 1.0f, 0.0f, alpha, c1, c2);
+          const float pe = pe_value3(Sx[n], Sxx[n], Sxy[n], R[(j - 1) % 3].xc[n], wy, kid, alpha, c1, c2);
           if (pe < best) { best = pe; sel = n; }
         }
 #if COLVO_FWD_M_SMEM
@@ -288,12 +312,12 @@ __global__ void __launch_bounds__(kFwdThreads, COLVO_MINB_FWD)
     cp_async_wait_all();
     __syncthreads();              // scale k landed everywhere; every warp is done with the other buffer
     if (k + 1 < P.S) stage_scale(k + 1, buf ^ 1);
-    float la[NS], lb[NS], ga[NS], gb[NS];
+    CalK cal[NS];
+    float ga[NS], gb[NS];
 #pragma unroll
     for (int n = 0; n < NS; ++n) {
       const int bnk = (b * P.N + n) * P.S + k;
-      la[n] = __ldg(ab + 2 * bnk);
-      lb[n] = __ldg(ab + 2 * bnk + 1);
+      cal[n] = make_calk(__ldg(ab + 2 * bnk), __ldg(ab + 2 * bnk + 1));
       ga[n] = gb[n] = 0.f;
     }
     const long long bk = (long long)b * P.S + k;
@@ -336,9 +360,10 @@ __global__ void __launch_bounds__(kFwdThreads, COLVO_MINB_FWD)
             }
           }
           const RowH<NS>& C = R[(j - 1) % 3];
+          winy_derive(wy, c1, c2);
 #pragma unroll
           for (int n = 0; n < NS; ++n) {
-            const float pe = pe_value(Sx[n], Sxx[n], Sxy[n], C.xc[n], wy, la[n], lb[n], alpha, c1, c2);
+            const float pe = pe_value3(Sx[n], Sxx[n], Sxy[n], C.xc[n], wy, cal[n], alpha, c1, c2);
             if (pe < best) { best = pe; sel = NS + n; }
           }
           loss_acc += best;
@@ -357,9 +382,9 @@ __global__ void __launch_bounds__(kFwdThreads, COLVO_MINB_FWD)
                 wSxy[c] = w1 ? Sxy[NS - 1][c] : Sxy[0][c];
                 wxc[c] = w1 ? C.xc[NS - 1][c] : C.xc[0][c];
               }
-              const float wa = w1 ? la[NS - 1] : la[0], wb = w1 ? lb[NS - 1] : lb[0];
+              const CalK wk = make_calk(w1 ? cal[NS - 1].a : cal[0].a, w1 ? cal[NS - 1].b : cal[0].b);
               float dpa = 0.f, dpb = 0.f;
-              pe_adjoint(wSx, wSxx, wSxy, wxc, wy, wa, wb, alpha, c1, c2, ca, cb, cg, dpa, dpb);
+              pe_adjoint(wSx, wSxx, wSxy, wxc, wy, wk, alpha, c1, c2, ca, cb, cg, dpa, dpb);
               if (w1) { ga[NS - 1] += dpa; gb[NS - 1] += dpb; }
               else { ga[0] += dpa; gb[0] += dpb; }
             }
@@ -389,7 +414,7 @@ __global__ void __launch_bounds__(kFwdThreads, COLVO_MINB_FWD)
 
   // per-tile partials: slot 0 = loss, slots 1.. = dL/da, dL/db per warped frame
   {
-    const double s = warp_sum((double)loss_acc);
+    const double s = warp_sum((double)(loss_acc * (1.0f / 3.0f)));      // candidates were compared as 3 * pe
     if (lane == 0) sm.red[wid * NV] = s;
   }
   __syncthreads();
