@@ -200,7 +200,18 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_STATS)
   const int bk = blockIdx.y, k = bk % P.S, b = bk / P.S;
   const Cam cam = load_cam(P, b);
   const float* Dk = P.depth[k] + (long long)b * P.depth_bs[k];
-  const Img<PK> tg = img_at<PK>(P, P.tgt, b * P.tgt_bf);
+  Img<PK> tg = img_at<PK>(P, P.tgt, b * P.tgt_bf);
+  // Loop-invariant bases, materialised once and hidden from the optimiser (which otherwise re-derives the 64-bit
+  // frame offsets per use under this kernel's 64-register cap); everything inside the loop is base + 32-bit offset:
+  // source n's frame sits src_noff elements behind source 0's, output frame (b, n, k) sits n * S * HW behind (b, 0, k).
+  Img<PK> src0 = img_at<PK>(P, P.srcs, b * P.src_bf);
+  const int src_noff = (int)(P.src_nf * P.frame_el);
+  const unsigned out_nstride = (unsigned)P.S * (unsigned)P.HW, hw = P.HW;
+  const long long out_bk = (long long)(b * P.N * P.S + k) * P.HW;
+  uint8_t* valid_b = valid_out ? valid_out + out_bk : nullptr;
+  float4* iw_b = iw_out ? iw_out + out_bk : nullptr;
+  float4* geo_b = geo_out ? geo_out + out_bk : nullptr;
+  asm volatile("" : "+l"(tg.p), "+l"(src0.p), "+l"(valid_b), "+l"(iw_b), "+l"(geo_b));
   Pose pose[NS];
 #pragma unroll
   for (int n = 0; n < NS; ++n) pose[n] = load_pose(P, b, n);
@@ -220,22 +231,20 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_STATS)
         tg.load3(pix, yv);
         y0 = yv[0]; y1 = yv[1]; y2 = yv[2];
       } else {
-        y0 = __ldg(tg.p + pix); y1 = __ldg(tg.p + P.HW + pix); y2 = __ldg(tg.p + 2 * P.HW + pix);
+        const unsigned upix = pix;
+        y0 = __ldg(tg.p + upix); y1 = __ldg(tg.p + (upix + hw)); y2 = __ldg(tg.p + (upix + 2 * hw));
       }
 #pragma unroll
       for (int n = 0; n < NS; ++n) {
-        // (built per use on purpose: a hoisted 64-bit base costs this 64-register kernel more than re-deriving it)
-        const Img<PK> src = img_at<PK>(P, P.srcs, b * P.src_bf + n * P.src_nf);
         Geo g; Taps t; Texels tx; float x[3];
-        warp_sample<PK>(P, src, cam, pose[n], rx, ry, D, g, t, tx, x);
-        const int bnk = (b * P.N + n) * P.S + k;
-        if (valid_out) valid_out[(long long)bnk * P.HW + pix] = g.valid ? 1 : 0;
+        warp_sample<PK>(P, src0, cam, pose[n], rx, ry, D, g, t, tx, x, n * src_noff);
+        const unsigned opix = (unsigned)pix + n * out_nstride;
+        if (valid_b) valid_b[opix] = g.valid ? 1 : 0;
         // raw warped frame, re-used by k_photo_fwd instead of warping again (+halo): one 16-byte texel
-        if (iw_out) iw_out[(long long)bnk * P.HW + pix] = make_float4(x[0], x[1], x[2], 0.f);
+        if (iw_b) iw_b[opix] = make_float4(x[0], x[1], x[2], 0.f);
         // the projection itself, for the backward (valid rides in the mantissa LSB of the depth)
-        if (geo_out)
-          geo_out[(long long)bnk * P.HW + pix] =
-              make_float4(g.u, g.v, g.iz, __uint_as_float((__float_as_uint(D) & ~1u) | (g.valid ? 1u : 0u)));
+        if (geo_b)
+          geo_b[opix] = make_float4(g.u, g.v, g.iz, __uint_as_float((__float_as_uint(D) & ~1u) | (g.valid ? 1u : 0u)));
         if (g.valid) {
           acc[NA * n + 0] += 3.0;
           acc[NA * n + 1] += (double)(x[0] + x[1] + x[2]);

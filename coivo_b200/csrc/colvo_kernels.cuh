@@ -164,10 +164,10 @@ __device__ __forceinline__ Img<true> img_at<true>(const KP& P, const void* base,
 // `src` is the [3][H][W] plane set of one source frame; offsets stay 32-bit (3*HW < 2^31).
 template <bool PK>
 __device__ __forceinline__ void warp_sample(const KP& P, const Img<PK>& src, const Cam& cam, const Pose& pose, float rx,
-                                            float ry, float D, Geo& g, Taps& t, Texels& tx, float (&x)[3]) {
+                                            float ry, float D, Geo& g, Taps& t, Texels& tx, float (&x)[3], int foff = 0) {
   g = reproject_ray(rx, ry, D, cam, pose, P.W, P.H, P.eps_proj, P.z_min);
   t = make_taps(g.u, g.v, P.W, P.H);
-  const int r0 = t.y0 * P.W, r1 = t.y1 * P.W;
+  const int r0 = foff + t.y0 * P.W, r1 = foff + t.y1 * P.W;     // foff: element offset of the frame from src.p
   src.load_taps(r0 + t.x0, r0 + t.x1, r1 + t.x0, r1 + t.x1, tx);
 #pragma unroll
   for (int c = 0; c < 3; ++c) x[c] = bilerp(tx.i00[c], tx.i01[c], tx.i10[c], tx.i11[c], t.wx, t.wy);
