@@ -15,6 +15,9 @@
 #ifndef COLVO_MINB_STATS
 #define COLVO_MINB_STATS 4
 #endif
+#ifndef COLVO_STATS_UNROLL  // pixels of the statistics loop in flight per thread
+#define COLVO_STATS_UNROLL 4
+#endif
 #ifndef COLVO_Y_REGS        // 1: keep the 3x3 target window of the own pixel in registers (27 regs)
 #define COLVO_Y_REGS 0
 #endif
@@ -220,7 +223,8 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_STATS)
   double acc[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) acc[i] = 0.0;
-#pragma unroll 2
+  constexpr int kUnroll = COLVO_STATS_UNROLL;
+#pragma unroll kUnroll
   for (int i = 0; i < kStatPPT; ++i) {
     if (pix < P.HW) {
       const float rx = ray_x(px, cam), ry = ray_y(py, cam);

@@ -17,7 +17,10 @@ constexpr int kFwdWarps = 4;     // warps per CTA
 constexpr int kFwdRows = 4;      // window rows per warp
 constexpr int kFwdThreads = kFwdWarps * 32;
 constexpr int kFwdTileH = kFwdWarps * kFwdRows;   // 16
-constexpr int kStatPPT = 8;      // pixels per thread in the LCC statistics pass
+#ifndef COLVO_STAT_PPT
+#define COLVO_STAT_PPT 8
+#endif
+constexpr int kStatPPT = COLVO_STAT_PPT;   // pixels per thread in the LCC statistics pass
 constexpr int kStatVals = 6;     // per (frame, chunk): n, Sx, Sy, Sxx, Sxy, sum of geometric-consistency diffs
 constexpr int kSmBW = 64, kSmBH = 16; // full-resolution pixels per smoothness block (k_smooth)
 constexpr int kSmVals = 4;            // per block and scale: sum over x edges, sum over y edges, sum s*d, sum d

@@ -5,9 +5,9 @@ from coivo_b200 import _lib
 
 VARIANTS = {
     "base": [],
-    "pipe2": ["COLVO_BWD_PIPE=1", "COLVO_MINB_BWD=2"],
-    "pipe3": ["COLVO_BWD_PIPE=1", "COLVO_MINB_BWD=3"],
-    "b2": ["COLVO_MINB_BWD=2"],
+    "p4u4": ["COLVO_STAT_PPT=4"],
+    "p4u2": ["COLVO_STAT_PPT=4", "COLVO_STATS_UNROLL=2"],
+    "p16u4": ["COLVO_STAT_PPT=16"],
 }
 out = os.path.join(os.path.dirname(_lib.PKG_DIR), "build", "variants")
 os.makedirs(out, exist_ok=True)
