@@ -14,9 +14,12 @@ constexpr int kTileW = 32;       // one warp = one tile row: coalesced 128 B row
 constexpr int kTileH = 8;
 // forward tile kernel (k_photo_fwd): every warp walks down a strip of windows, one window column per lane
 constexpr int kFwdWarps = 4;     // warps per CTA
-constexpr int kFwdRows = 4;      // window rows per warp
+#ifndef COLVO_FWD_ROWS       // 3 rows: 50 KB of shared memory and 128 registers -> 4 CTAs (16 warps) per SM; 4 rows: 66 KB / 167
+#define COLVO_FWD_ROWS 3     // registers -> 3 CTAs; measured 128 vs 133 us (profiles/r1_variants_v21.log)
+#endif
+constexpr int kFwdRows = COLVO_FWD_ROWS;   // window rows per warp
 constexpr int kFwdThreads = kFwdWarps * 32;
-constexpr int kFwdTileH = kFwdWarps * kFwdRows;   // 16
+constexpr int kFwdTileH = kFwdWarps * kFwdRows;   // 12
 #ifndef COLVO_STAT_PPT
 #define COLVO_STAT_PPT 8
 #endif

@@ -1,7 +1,7 @@
 // k_photo_fwd: the fused forward tile kernel, sm_100a.
 //
-// One CTA = 4 warps = one 32 x 16 tile of windows of one triplet.  Every warp walks DOWN a strip of
-// 4 window rows with one window column per lane: for each data row it forms the horizontal 3-sums
+// One CTA = 4 warps = one 32 x 12 tile of windows of one triplet.  Every warp walks DOWN a strip of
+// 3 window rows with one window column per lane: for each data row it forms the horizontal 3-sums
 // of x, x^2 and x*y of both warped frames (texels (x0,x1,x2,-) read with LDS.128 from the staged
 // tile), keeps the last three rows of sums in registers and adds them vertically -- the separable
 // form of the 3x3 SSIM window, ~2.4x fewer issue slots than summing 9 taps per window.  Both sources
@@ -18,7 +18,7 @@
 #define COLVO_FWD_M_SMEM 1   // 0: recompute them in every scale's walk (50 KB per CTA, 4 CTAs / SM)
 #endif
 #ifndef COLVO_MINB_FWD
-#define COLVO_MINB_FWD (COLVO_FWD_M_SMEM ? 3 : 4)
+#define COLVO_MINB_FWD ((COLVO_FWD_M_SMEM && COLVO_FWD_ROWS > 3) ? 3 : 4)
 #endif
 
 namespace colvo {

@@ -5,9 +5,9 @@ from coivo_b200 import _lib
 
 VARIANTS = {
     "base": [],
-    "p4u4": ["COLVO_STAT_PPT=4"],
-    "p4u2": ["COLVO_STAT_PPT=4", "COLVO_STATS_UNROLL=2"],
-    "p16u4": ["COLVO_STAT_PPT=16"],
+    "r3m4": ["COLVO_FWD_ROWS=3", "COLVO_MINB_FWD=4"],
+    "r2m5": ["COLVO_FWD_ROWS=2", "COLVO_MINB_FWD=5"],
+    "r6m2": ["COLVO_FWD_ROWS=6", "COLVO_MINB_FWD=2"],
 }
 out = os.path.join(os.path.dirname(_lib.PKG_DIR), "build", "variants")
 os.makedirs(out, exist_ok=True)
