@@ -12,6 +12,9 @@
 //   k_pose_final     deterministic reduction of the pose-gradient partials
 #include "colvo_kernels.cuh"
 
+#ifndef COLVO_BWD_L2_HINT    // 1: load the saved coefficients / projections (each read once) with L2 evict-first priority (measured: no effect)
+#define COLVO_BWD_L2_HINT 0
+#endif
 #ifndef COLVO_BWD_PIPE       // 1: software pipeline of the per-scale loads: the saved projection of scale k+1 is fetched during
 #define COLVO_BWD_PIPE 0     //    scale k, and the taps of scale k are issued BEFORE its coefficient gather (more registers)
 #endif
@@ -140,6 +143,9 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_BWD)
 
   // Coefficient tile of scale k (+1 halo; zeros outside the image), fetched with cp.async one scale ahead so its
   // global latency hides behind the previous scale's arithmetic.
+#if COLVO_BWD_L2_HINT
+  const unsigned long long l2pol = l2_evict_first_policy();
+#endif
   auto stage_coef = [&](int k) {
     float4* cbf = coef[k & 1];
     const float4* cin = reinterpret_cast<const float4*>(coef_in) + (long long)(b * P.S + k) * P.HW * 3;
@@ -149,7 +155,13 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_BWD)
       const bool on = gy >= 0 && gy < P.H && gx >= 0 && gx < P.W;
       const float4* p = on ? cin + (gy * P.W + gx) : cin;
 #pragma unroll
-      for (int ch = 0; ch < 3; ++ch) cp_async16(cbf + idx * 3 + ch, p + (long long)ch * P.HW, on);
+      for (int ch = 0; ch < 3; ++ch) {
+#if COLVO_BWD_L2_HINT
+        cp_async16_hint(cbf + idx * 3 + ch, p + (long long)ch * P.HW, on, l2pol);
+#else
+        cp_async16(cbf + idx * 3 + ch, p + (long long)ch * P.HW, on);
+#endif
+      }
     }
     mbar_arrive_cp_async(&mbar[k & 1]);      // this thread's share of full[k & 1]
   };
@@ -196,7 +208,13 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_BWD)
     }
 #else
 #pragma unroll
-    for (int n = 0; n < NS; ++n) gt[n] = __ldg(geo_in + (long long)((b * P.N + n) * P.S + k) * P.HW + qo);
+    for (int n = 0; n < NS; ++n) {
+#if COLVO_BWD_L2_HINT
+      gt[n] = ldg_f4_hint(geo_in + (long long)((b * P.N + n) * P.S + k) * P.HW + qo, l2pol);
+#else
+      gt[n] = __ldg(geo_in + (long long)((b * P.N + n) * P.S + k) * P.HW + qo);
+#endif
+    }
     const int own_sel = __ldg(sel + ((long long)b * P.S + k) * P.HW + qo);
 #endif
     // Two transaction barriers per buffer instead of a block barrier per scale: the copies of scale k+1 are issued

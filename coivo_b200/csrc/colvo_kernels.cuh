@@ -191,6 +191,24 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool pr
   const int sz = pred ? 16 : 0;
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(sz));
 }
+// L2 eviction-priority hints for data that is streamed exactly once: it should not displace the lines the kernel
+// keeps hitting (the scatter accumulator of the backward is read-modify-written ~32 times per texel by L2 atomics)
+__device__ __forceinline__ unsigned long long l2_evict_first_policy() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void cp_async16_hint(void* smem, const void* gmem, bool pred, unsigned long long pol) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  const int sz = pred ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;\n" ::"r"(sa), "l"(gmem), "r"(sz), "l"(pol));
+}
+__device__ __forceinline__ float4 ldg_f4_hint(const float4* p, unsigned long long pol) {
+  float4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;\n"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+  return v;
+}
 // the same with the 32-bit shared-window address already at hand (hoisted out of an unrolled staging loop)
 __device__ __forceinline__ void cp_async16_s(unsigned saddr, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(gmem));

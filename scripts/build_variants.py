@@ -5,9 +5,7 @@ from coivo_b200 import _lib
 
 VARIANTS = {
     "base": [],
-    "r3m4": ["COLVO_FWD_ROWS=3", "COLVO_MINB_FWD=4"],
-    "r2m5": ["COLVO_FWD_ROWS=2", "COLVO_MINB_FWD=5"],
-    "r6m2": ["COLVO_FWD_ROWS=6", "COLVO_MINB_FWD=2"],
+    "nohint": ["COLVO_BWD_L2_HINT=0"],
 }
 out = os.path.join(os.path.dirname(_lib.PKG_DIR), "build", "variants")
 os.makedirs(out, exist_ok=True)
