@@ -64,6 +64,7 @@ void fill_params(KP& P, const ColvoDesc* d) {
   P.K_bs = 9; P.T_ns = 16; P.T_bs = 16 * d->N;
   P.tiles_x = div_up(d->W, kTileW);
   P.tiles_y = div_up(d->H, kTileH);
+  P.btiles_y = div_up(d->H, kBwdTileH);
   P.ftiles_x = div_up(d->W, 32);
   P.ftiles_y = div_up(d->H, kFwdTileH);
   P.sm_blocks = div_up(d->W, kSmBW) * div_up(d->H, kSmBH);
@@ -94,7 +95,7 @@ size_t carve_fwd(const ColvoDesc* d, void* ws, FwdBuffers& F) {
 
 size_t carve_bwd(const ColvoDesc* d, void* ws, BwdBuffers& Bw) {
   Carver c(ws);
-  const size_t tiles = (size_t)div_up(d->W, kTileW) * div_up(d->H, kTileH);
+  const size_t tiles = (size_t)div_up(d->W, kTileW) * div_up(d->H, kBwdTileH);
   const size_t HW = (size_t)d->H * d->W;
   Bw.dDhat[0] = nullptr;
   for (int k = 1; k < kMaxS; ++k) Bw.dDhat[k] = (k < d->S) ? c.take<float>((size_t)d->B * HW) : nullptr;

@@ -28,12 +28,12 @@
 #define COLVO_EXP_NORED 0
 #endif
 #ifndef COLVO_MINB_BWD      // CTAs per SM the register allocator must allow -- tuned on B200, see DESIGN.md
-#define COLVO_MINB_BWD 3
+#define COLVO_MINB_BWD (24 / COLVO_BWD_TILE_H)     // 24 warps per SM at 80 registers
 #endif
 
 namespace colvo {
 
-constexpr int kCH = kTileH + 2, kCW = kTileW + 2;   // tile + 1-pixel halo (window centres)
+constexpr int kCH = kBwdTileH + 2, kCW = kTileW + 2;   // tile + 1-pixel halo (window centres)
 constexpr int kCN = kCH * kCW;
 
 // smoothness gradient of one depth texel from the saved adjoint field (grad_loss folded in by the caller)
@@ -57,7 +57,7 @@ struct BwdConst {          // per warped frame (n, k), built once per CTA
 };
 
 template <int NS, bool GEO, bool PK>
-__global__ void __launch_bounds__(kThreads, COLVO_MINB_BWD)
+__global__ void __launch_bounds__(kBwdThreads, COLVO_MINB_BWD)
     k_photo_bwd(KP P, const float* __restrict__ grad_loss, const uint8_t* __restrict__ sel,
                 const double* __restrict__ saved_frame, const double* __restrict__ saved_scale,
                 const float* __restrict__ s_field0, const float* __restrict__ coef_in,
@@ -69,16 +69,16 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_BWD)
   float4 (*coef)[kCN * 3] = reinterpret_cast<float4 (*)[kCN * 3]>(smem_raw);   // [2]: (ca, cb, cg, n) per window
                                                                                // centre and channel, double-buffered over k
   double* red = reinterpret_cast<double*>(smem_raw + sizeof(float4) * 2 * kCN * 3);
-  BwdConst (*cst)[kMaxS] = reinterpret_cast<BwdConst (*)[kMaxS]>(red + (kThreads / 32) * NS * 12);   // [NS][kMaxS]
+  BwdConst (*cst)[kMaxS] = reinterpret_cast<BwdConst (*)[kMaxS]>(red + (kBwdThreads / 32) * NS * 12);   // [NS][kMaxS]
   float (*pose_s)[12] = reinterpret_cast<float (*)[12]>(cst + NS);                                   // [NS]: R row-major, t
   float* cst_sm = reinterpret_cast<float*>(pose_s + NS);   // scale 0: 1/(mean+eps), sum(s d)/(n (mean+eps)^2)
   // full[i]: the copies into coefficient buffer i have landed (cp.async arrivals); empty[i]: every thread is done reading it
   unsigned long long* mbar = reinterpret_cast<unsigned long long*>(smem_raw + sizeof(float4) * 2 * kCN * 3 +
-                                                                   sizeof(double) * (kThreads / 32) * NS * 12 + 1024);
+                                                                   sizeof(double) * (kBwdThreads / 32) * NS * 12 + 1024);
 
   pdl_trigger();         // the epilogue launch may become resident while this kernel drains
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
-  const int b = blockIdx.z, x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
+  const int b = blockIdx.z, x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kBwdTileH;
   const int px = x0 + tx, py = y0 + ty;
   const bool in_img = (px < P.W) && (py < P.H);
   const int qx = imin(px, P.W - 1), qy = imin(py, P.H - 1);             // addressable stand-in when outside
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_BWD)
     const float* t = P.T + (long long)b * P.T_bs + (long long)n * P.T_ns;
     pose_s[n][j] = (j < 9) ? __ldg(t + 4 * (j / 3) + (j % 3)) : __ldg(t + 4 * (j - 9) + 3);
   }
-  if (tid == 64) {
+  if (tid == kBwdThreads - 1) {
     const double* sc = saved_scale + (long long)(b * P.S) * kSavedPerScale;
     const double me = sc[0] + (double)P.eps_disp;
     cst_sm[0] = (float)(1.0 / me);
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_BWD)
   auto stage_coef = [&](int k) {
     float4* cbf = coef[k & 1];
     const float4* cin = reinterpret_cast<const float4*>(coef_in) + (long long)(b * P.S + k) * P.HW * 3;
-    for (int idx = tid; idx < kCN; idx += kThreads) {
+    for (int idx = tid; idx < kCN; idx += kBwdThreads) {
       const int r = idx / kCW, c = idx - r * kCW;
       const int gy = y0 - 1 + r, gx = x0 - 1 + c;
       const bool on = gy >= 0 && gy < P.H && gx >= 0 && gx < P.W;
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_BWD)
   };
   if (tid == 0) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) mbar_init(&mbar[i], kThreads);
+    for (int i = 0; i < 4; ++i) mbar_init(&mbar[i], kBwdThreads);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();       // barriers initialised; per-frame constants visible
@@ -357,18 +357,18 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_BWD)
   }
 
   // ---- per-tile pose-gradient partials (fp64: sums of terms of both signs) ----
-  const int blk = (b * P.tiles_y + blockIdx.y) * P.tiles_x + blockIdx.x;
+  const int blk = (b * P.btiles_y + blockIdx.y) * P.tiles_x + blockIdx.x;
   __syncthreads();                                   // the coefficient buffers are free: reuse them as slot storage
-  float* slots = reinterpret_cast<float*>(smem_raw); // [NS*12][kThreads] <= 24 KB of the 32 KB coefficient area
+  float* slots = reinterpret_cast<float*>(smem_raw); // [NS*12][kBwdThreads] <= 24 KB of the 32 KB coefficient area
 #pragma unroll
   for (int n = 0; n < NS; ++n) {
     float gp[12];
     pose_grad_expand(pw[n], pt[n], own_rx, own_ry, gp);
 #pragma unroll
-    for (int j = 0; j < 12; ++j) slots[(n * 12 + j) * kThreads + tid] = in_img ? gp[j] : 0.f;
+    for (int j = 0; j < 12; ++j) slots[(n * 12 + j) * kBwdThreads + tid] = in_img ? gp[j] : 0.f;
   }
   __syncthreads();
-  block_sum_slots<NS * 12>(slots, red, [&](int slot, double v) { pose_part[(long long)blk * (NS * 12) + slot] = v; });
+  block_sum_slots<NS * 12, kBwdThreads>(slots, red, [&](int slot, double v) { pose_part[(long long)blk * (NS * 12) + slot] = v; });
 }
 
 // ------------------------------------------------------------------------------------------
@@ -407,7 +407,7 @@ __device__ __forceinline__ void pose_final_block(const KP& P, const PoseFinalArg
     return;
   }
   const int bn = blk, b = bn / P.N, n = bn % P.N;
-  const int tiles = P.tiles_x * P.tiles_y, nv = P.N * 12;
+  const int tiles = P.tiles_x * P.btiles_y, nv = P.N * 12;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   for (int j = wid; j < 16; j += kThreads / 32) {
     if (j < 12) {
@@ -550,7 +550,7 @@ __global__ void __launch_bounds__(kThreads) k_zero(float4* __restrict__ a, long 
 
 template <int NS>
 static size_t photo_bwd_smem() {
-  return sizeof(float4) * 2 * kCN * 3 + sizeof(double) * (kThreads / 32) * NS * 12 +
+  return sizeof(float4) * 2 * kCN * 3 + sizeof(double) * (kBwdThreads / 32) * NS * 12 +
          1024 /* per-frame constants, poses */ + 4 * sizeof(unsigned long long) /* mbarriers */;
 }
 
@@ -569,18 +569,18 @@ cudaError_t launch_backward(const KP& P, const BwdBuffers& Wk, const float* grad
     const long long nb = zero_sd ? (long long)P.B * P.N * P.HW / 4 : 0;
     k_zero<<<148 * 4, kThreads, 0, st>>>(Wk.gsrc4, na, reinterpret_cast<float4*>(grad_src_depth), nb);
   }
-  dim3 grid(P.tiles_x, P.tiles_y, P.B);
+  dim3 grid(P.tiles_x, P.btiles_y, P.B);
   {
     ScopedKernelTimer tm(2, st);
     // opting in to > 48 KB of dynamic shared memory is a per-function, per-device attribute: cheap and idempotent
     auto launch = [&](auto kern, size_t smem) {
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (zeroed)
-        e = launch_pdl(kern, grid, dim3(kThreads), smem, st, P, grad_loss, sel, (const double*)sv.frame, (const double*)sv.scale,
+        e = launch_pdl(kern, grid, dim3(kBwdThreads), smem, st, P, grad_loss, sel, (const double*)sv.frame, (const double*)sv.scale,
                        (const float*)sv.s_field[0], (const float*)sv.coef, (const float4*)sv.geo, grad_depth[0], Wk.dDhat[1],
                        Wk.dDhat[2], Wk.dDhat[3], grad_srcs ? Wk.gsrc4 : nullptr, grad_src_depth, Wk.pose_part);
       else
-        kern<<<grid, kThreads, smem, st>>>(P, grad_loss, sel, sv.frame, sv.scale, sv.s_field[0], sv.coef, sv.geo, grad_depth[0],
+        kern<<<grid, kBwdThreads, smem, st>>>(P, grad_loss, sel, sv.frame, sv.scale, sv.s_field[0], sv.coef, sv.geo, grad_depth[0],
                                            Wk.dDhat[1], Wk.dDhat[2], Wk.dDhat[3], grad_srcs ? Wk.gsrc4 : nullptr, grad_src_depth,
                                            Wk.pose_part);
     };

@@ -12,6 +12,12 @@ constexpr int kMaxN = 2;
 constexpr int kThreads = 256;
 constexpr int kTileW = 32;       // one warp = one tile row: coalesced 128 B rows
 constexpr int kTileH = 8;
+// backward tile kernel (k_photo_bwd): 32 x kBwdTileH pixels, one thread each
+#ifndef COLVO_BWD_TILE_H
+#define COLVO_BWD_TILE_H 8
+#endif
+constexpr int kBwdTileH = COLVO_BWD_TILE_H;
+constexpr int kBwdThreads = 32 * kBwdTileH;
 // forward tile kernel (k_photo_fwd): every warp walks down a strip of windows, one window column per lane
 constexpr int kFwdWarps = 4;     // warps per CTA
 #ifndef COLVO_FWD_ROWS       // 3 rows: 50 KB of shared memory and 128 registers -> 4 CTAs (16 warps) per SM; 4 rows: 66 KB / 167
@@ -59,7 +65,8 @@ struct KP {
   long long frame_el;                // elements per frame in the storage format: 3*HW floats, or HW 8-byte texels
   long long depth_bs[kMaxS];
   int K_bs, T_bs, T_ns;
-  int tiles_x, tiles_y;               // 32 x 8 tiles of the backward kernel
+  int tiles_x, tiles_y;               // 32 x 8 tiles (consistency sweep; sizing of the forward partials)
+  int btiles_y;                       // rows of 32 x kBwdTileH tiles of the backward kernel
   int ftiles_x, ftiles_y;             // 32 x 16 tiles of the forward kernel
 };
 
@@ -320,13 +327,13 @@ __device__ __forceinline__ void block_reduce_store(TV (&v)[NV], TV* sm /* [kThre
 // reads: conflict-free), then 8 warp partials per slot are combined in a fixed order.  ~5x fewer
 // issue slots than NSLOT fp64 shuffle trees.  `part` is (kThreads/32) * NSLOT doubles of scratch.
 // Call with all threads after the slots are written and a __syncthreads(); result in out[s], s < NSLOT.
-template <int NSLOT, typename F>
+template <int NSLOT, int NT, typename F>
 __device__ __forceinline__ void block_sum_slots(const float* slots, double* part, F&& emit) {
-  constexpr int NW = kThreads / 32;
+  constexpr int NW = NT / 32;
   const int tid = threadIdx.x;
-  for (int item = tid; item < NSLOT * NW; item += kThreads) {
+  for (int item = tid; item < NSLOT * NW; item += NT) {
     const int s = item / NW, w = item - s * NW;
-    const float* p = slots + s * kThreads + w * 32;
+    const float* p = slots + s * NT + w * 32;
     double acc = 0.0;
 #pragma unroll 8
     for (int l = 0; l < 32; ++l) acc += (double)p[(l + tid) & 31];

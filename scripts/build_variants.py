@@ -5,7 +5,9 @@ from coivo_b200 import _lib
 
 VARIANTS = {
     "base": [],
-    "nohint": ["COLVO_BWD_L2_HINT=0"],
+    "t4": ["COLVO_BWD_TILE_H=4"],
+    "t6": ["COLVO_BWD_TILE_H=6"],
+    "t2": ["COLVO_BWD_TILE_H=2"],
 }
 out = os.path.join(os.path.dirname(_lib.PKG_DIR), "build", "variants")
 os.makedirs(out, exist_ok=True)
