@@ -243,15 +243,24 @@ int colvo_debug_time_kernel(int which, void* ev_start, void* ev_stop) {
 }
 
 // ---- consistency sweep ----------------------------------------------------------------------
+// pairs whose warped frames share one pass of the scratch buffer: at most 256 MB of texels
+static int consistency_pairs_per_pass(int F, int H, int W) {
+  const long long per = (long long)H * W * (long long)sizeof(float4);
+  long long n = (256ll << 20) / per;
+  if (n < 1) n = 1;
+  if (n > F - 1) n = F - 1;
+  return (int)n;
+}
 static size_t carve_consistency(int F, int H, int W, void* ws, double** stat, int* chunks, double** pe_part,
-                                float** ab) {
+                                float** ab, float4** iw) {
   Carver c(ws);
   const size_t Pn = (size_t)(F - 1);
-  const size_t tiles = (size_t)div_up(W, kTileW) * div_up(H, kTileH);
+  const size_t tiles = (size_t)div_up(W, 32) * div_up(H, kFwdTileH);
   *chunks = div_up(H * W, kThreads * kStatPPT);
   *stat = c.take<double>(Pn * (*chunks) * kStatVals);
   *pe_part = c.take<double>(Pn * tiles * 2);
   *ab = c.take<float>(Pn * 2);
+  *iw = c.take<float4>((size_t)consistency_pairs_per_pass(F, H, W) * H * W);
   return c.off;
 }
 
@@ -260,8 +269,9 @@ int colvo_consistency_workspace_bytes(int32_t F, int32_t H, int32_t W, size_t* b
   if (F < 2 || H < 2 || W < 2 || F - 1 > 65535) return COLVO_E_BAD_DESC;
   double *a, *b;
   float* c;
+  float4* iw;
   int ch;
-  *bytes = carve_consistency(F, H, W, nullptr, &a, &ch, &b, &c);
+  *bytes = carve_consistency(F, H, W, nullptr, &a, &ch, &b, &c, &iw);
   return 0;
 }
 
@@ -273,8 +283,9 @@ int colvo_consistency(int32_t F, int32_t H, int32_t W, uint32_t flags, const flo
   if ((uintptr_t)ws & 255u) return COLVO_E_MISALIGNED;
   double *stat, *pe_part;
   float* ab;
+  float4* iw;
   int chunks;
-  if (carve_consistency(F, H, W, ws, &stat, &chunks, &pe_part, &ab) > ws_bytes) return COLVO_E_WORKSPACE;
+  if (carve_consistency(F, H, W, ws, &stat, &chunks, &pe_part, &ab, &iw) > ws_bytes) return COLVO_E_WORKSPACE;
   ColvoDesc d;
   int rc = colvo_desc_init(&d, F - 1, 1, 1, H, W, flags & COLVO_F_LCC);
   if (rc) return rc;
@@ -292,7 +303,8 @@ int colvo_consistency(int32_t F, int32_t H, int32_t W, uint32_t flags, const flo
   P.T = T;
   P.T_bs = 16;
   P.T_ns = 0;
-  return (int)launch_consistency(P, stat, chunks, pe_part, ab, out, static_cast<cudaStream_t>(stream));
+  return (int)launch_consistency(P, stat, chunks, pe_part, ab, out, iw, consistency_pairs_per_pass(F, H, W),
+                                 static_cast<cudaStream_t>(stream));
 }
 
 // ---- end-to-end step on host buffers ----------------------------------------------------------

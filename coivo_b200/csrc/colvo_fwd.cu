@@ -18,9 +18,6 @@
 #ifndef COLVO_STATS_UNROLL  // pixels of the statistics loop in flight per thread
 #define COLVO_STATS_UNROLL 4
 #endif
-#ifndef COLVO_Y_REGS        // 1: keep the 3x3 target window of the own pixel in registers (27 regs)
-#define COLVO_Y_REGS 0
-#endif
 
 namespace colvo {
 
@@ -245,7 +242,7 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_STATS)
         const unsigned opix = (unsigned)pix + n * out_nstride;
         if (valid_b) valid_b[opix] = g.valid ? 1 : 0;
         // raw warped frame, re-used by k_photo_fwd instead of warping again (+halo): one 16-byte texel
-        if (iw_b) iw_b[opix] = make_float4(x[0], x[1], x[2], 0.f);
+        if (iw_b) iw_b[opix] = make_float4(x[0], x[1], x[2], g.valid ? 1.f : 0.f);
         // the projection itself, for the backward (valid rides in the mantissa LSB of the depth)
         if (geo_b)
           geo_b[opix] = make_float4(g.u, g.v, g.iz, __uint_as_float((__float_as_uint(D) & ~1u) | (g.valid ? 1u : 0u)));
@@ -318,75 +315,6 @@ __global__ void __launch_bounds__(32)
       double* o = saved + (long long)bnk * kSavedPerFrame;
       o[0] = n; o[1] = mx; o[2] = my; o[3] = inv_nvar; o[4] = (double)af; o[5] = (double)bf; o[6] = 0.0; o[7] = 0.0;
     }
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// 3x3-window helpers of the consistency sweep's tile kernel (k_consistency_pe below): one window per
-// thread over a 32x8 tile (+1 halo) in shared memory.  The training loss uses the strip kernel in
-// colvo_photo_fwd.cuh instead.
-constexpr int kFH = kTileH + 2, kFW = kTileW + 2;   // tile + 1-pixel SSIM halo
-constexpr int kFN = kFH * kFW;
-
-// The 3x3 target window of the own pixel: either 27 registers or re-read from the target tile.
-struct YWin {
-#if COLVO_Y_REGS
-  float v[3][9];
-#endif
-  const float* ys;      // [3][kFN] target tile in shared memory
-  int o;                // ty*kFW + tx
-  float mu[3], sg[3];   // window mean and variance of the target
-  __device__ __forceinline__ float at(int c, int j) const {
-#if COLVO_Y_REGS
-    return v[c][j];
-#else
-    return ys[c * kFN + o + (j / 3) * kFW + (j % 3)];
-#endif
-  }
-};
-
-__device__ __forceinline__ float pe_own(const float* __restrict__ xb /* [3][kFN] */, const YWin& y, float a, float b,
-                                        const KP& P, float* dpa, float* dpb, bool want_cf, Coef (&cf)[3]) {
-  float pe = 0.f;
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    float s = 0.f, sxx = 0.f, sxy = 0.f, xc = 0.f, yc = 0.f;
-#pragma unroll
-    for (int j = 0; j < 9; ++j) {
-      const float v = xb[c * kFN + y.o + (j / 3) * kFW + (j % 3)];
-      const float w = y.at(c, j);
-      if (j == 4) { xc = v; yc = w; }
-      s += v;
-      sxx = fmaf(v, v, sxx);
-      sxy = fmaf(v, w, sxy);
-    }
-    const float i9 = 1.0f / 9.0f;
-    pe += pe_channel(s * i9, sxx * i9, sxy * i9, y.mu[c], y.sg[c], xc, yc, a, b, P.alpha, P.c1, P.c2, dpa, dpb, want_cf,
-                     cf[c]);
-  }
-  return pe * (1.0f / 3.0f);
-}
-__device__ __forceinline__ float pe_own(const float* __restrict__ xb, const YWin& y, float a, float b, const KP& P) {
-  Coef unused[3];
-  return pe_own(xb, y, a, b, P, nullptr, nullptr, false, unused);
-}
-__device__ __forceinline__ void ywin_init(YWin& y, const float* ys, int own) {
-  y.ys = ys;
-  y.o = own;
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    float s = 0.f, ss = 0.f;
-#pragma unroll
-    for (int j = 0; j < 9; ++j) {
-      float v = ys[c * kFN + own + (j / 3) * kFW + (j % 3)];
-#if COLVO_Y_REGS
-      y.v[c][j] = v;
-#endif
-      s += v;
-      ss = fmaf(v, v, ss);
-    }
-    y.mu[c] = s * (1.0f / 9.0f);
-    y.sg[c] = ss * (1.0f / 9.0f) - y.mu[c] * y.mu[c];
   }
 }
 
@@ -512,54 +440,92 @@ __global__ void __launch_bounds__(kThreads)
 
 // ------------------------------------------------------------------------------------------
 // Consistency sweep (BASELINE config 5): per pair, mean pe over valid pixels.  N = 1, S = 1.
-__global__ void __launch_bounds__(kThreads, 2)
-    k_consistency_pe(KP P, const float* __restrict__ ab, double* __restrict__ pe_part) {
-  __shared__ float ys[3 * kFN];
-  __shared__ float xs[3 * kFN];
-  __shared__ unsigned char vs[kFN];
-  __shared__ double red[(kThreads / 32) * 2];
-  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
-  const int b = blockIdx.z, x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
-  const int px = x0 + tx, py = y0 + ty;
-  const bool in_img = (px < P.W) && (py < P.H);
-  const int own = ty * kFW + tx;
-  const float* tg = static_cast<const float*>(P.tgt) + b * P.tgt_bf * P.frame_el;
-  const Img<false> src = img_at<false>(P, P.srcs, b * P.src_bf);
-  const float* Dk = P.depth[0] + (long long)b * P.depth_bs[0];
-  const Cam cam = load_cam(P, b);
-  const Pose pose = load_pose(P, b, 0);
-  for (int idx = tid; idx < kFN; idx += kThreads) {
-    int r = idx / kFW, c = idx - r * kFW;
-    int ry = y0 - 1 + r, rx = x0 - 1 + c;
-    int gy = reflect_clamp(ry, P.H), gx = reflect_clamp(rx, P.W);
+// Same strip walk as k_photo_fwd (colvo_photo_fwd.cuh) over the warped frame k_warp_stats left in scratch
+// (texel .w = validity): one warp = 32 window columns x kFwdRows rows, separable 3x3 sums, value only.
+struct ConsSmem {
+  float4 y[kDN];
+  float4 x[kDN];
+  double red[kFwdWarps * 2];
+};
+__global__ void __launch_bounds__(kFwdThreads)
+    k_consistency_pe(KP P, const float* __restrict__ ab, const float4* __restrict__ iw, double* __restrict__ pe_part) {
+  __shared__ ConsSmem sm;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int b = blockIdx.z, x0 = blockIdx.x * 32, y0 = blockIdx.y * kFwdTileH;
+  const int px = x0 + lane;
+  {
+    const float* tg = static_cast<const float*>(P.tgt) + (long long)b * P.tgt_bf * P.frame_el;
+    const float4* xw = iw + (long long)b * P.HW;
+    asm volatile("" : "+l"(tg), "+l"(xw));
+    const unsigned say = (unsigned)__cvta_generic_to_shared(&sm.y[tid]), sax = (unsigned)__cvta_generic_to_shared(&sm.x[tid]);
+    const unsigned hw = P.HW;
 #pragma unroll
-    for (int ch = 0; ch < 3; ++ch) ys[ch * kFN + idx] = __ldg(tg + (ch * P.HW + gy * P.W + gx));
-    if (ry <= P.H && rx <= P.W) {
-      Geo g; Taps t; Texels tx4; float x[3];
-      warp_sample<false>(P, src, cam, pose, ray_x(gx, cam), ray_y(gy, cam), __ldg(Dk + gy * P.W + gx), g, t, tx4, x);
-      xs[idx] = x[0];
-      xs[kFN + idx] = x[1];
-      xs[2 * kFN + idx] = x[2];
-      vs[idx] = g.valid ? 1 : 0;
+    for (int j = 0; j < kStageRounds; ++j) {
+      const int idx = tid + j * kFwdThreads;
+      if (idx < kDN) {
+        const int r = idx / kDW, c = idx - r * kDW;
+        const unsigned go = reflect_clamp(y0 - 1 + r, P.H) * P.W + reflect_clamp(x0 - 1 + c, P.W);
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) cp_async4_s(say + (j * kFwdThreads * 4 + ch) * (unsigned)sizeof(float), tg + (go + ch * hw));
+        cp_async16_s(sax + j * kFwdThreads * (unsigned)sizeof(float4), xw + go);
+      }
+    }
+    cp_async_commit();
+    cp_async_wait_all();
+    __syncthreads();
+  }
+  const CalK cal = make_calk(__ldg(ab + 2 * b), __ldg(ab + 2 * b + 1));
+  const int trow0 = wid * kFwdRows;
+  double acc[2] = {0.0, 0.0};
+  RowH<1> R[3];
+  RowY Y[3];
+#pragma unroll
+  for (int j = 0; j < kFwdRows + 2; ++j) {
+    const int o = (trow0 + j) * kDW + lane;
+    row_sums<1, true>(R[j % 3], Y[j % 3], sm.y + o, sm.x + o, sm.x + o);
+    if (j >= 2) {
+      const int py = y0 + trow0 + j - 2;
+      // validity of the window's own pixel: the centre texel of the middle row
+      const bool valid = sm.x[(trow0 + j - 1) * kDW + lane + 1].w != 0.f;
+      if (py < P.H && px < P.W && valid) {
+        WinY wy;
+        float Sx[3], Sxx[3], Sxy[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float sy = Y[0].sy[c] + Y[1].sy[c] + Y[2].sy[c];
+          const float syy = Y[0].syy[c] + Y[1].syy[c] + Y[2].syy[c];
+          wy.muy[c] = sy * (1.0f / 9.0f);
+          wy.sgy[c] = fmaf(-wy.muy[c], wy.muy[c], syy * (1.0f / 9.0f));
+          wy.yc[c] = Y[(j - 1) % 3].yc[c];
+          Sx[c] = R[0].sx[0][c] + R[1].sx[0][c] + R[2].sx[0][c];
+          Sxx[c] = R[0].sxx[0][c] + R[1].sxx[0][c] + R[2].sxx[0][c];
+          Sxy[c] = R[0].sxy[0][c] + R[1].sxy[0][c] + R[2].sxy[0][c];
+        }
+        winy_derive(wy, P.c1, P.c2);
+        acc[0] += (double)(pe_value3(Sx, Sxx, Sxy, R[(j - 1) % 3].xc[0], wy, cal, P.alpha, P.c1, P.c2) * (1.0f / 3.0f));
+        acc[1] += 1.0;
+      }
     }
   }
-  __syncthreads();
-  double acc[2] = {0.0, 0.0};
-  if (in_img && vs[own + kFW + 1]) {
-    YWin yw;
-    ywin_init(yw, ys, own);
-    float pe = pe_own(xs, yw, __ldg(ab + 2 * b), __ldg(ab + 2 * b + 1), P);
-    acc[0] = (double)pe;
-    acc[1] = 1.0;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const double s = warp_sum(acc[i]);
+    if (lane == 0) sm.red[wid * 2 + i] = s;
   }
-  const int blk = (b * P.tiles_y + blockIdx.y) * P.tiles_x + blockIdx.x;
-  block_reduce_store<2, double>(acc, red, pe_part + (long long)blk * 2);
+  __syncthreads();
+  if (tid < 2) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < kFwdWarps; ++w) s += sm.red[w * 2 + tid];
+    const int blk = (b * P.ftiles_y + blockIdx.y) * P.ftiles_x + blockIdx.x;
+    pe_part[(long long)blk * 2 + tid] = s;
+  }
 }
 
 __global__ void __launch_bounds__(kThreads)
     k_consistency_final(KP P, const double* __restrict__ pe_part, const float* __restrict__ ab, float* __restrict__ out) {
   __shared__ double sm[(kThreads / 32) * 2];
-  const int b = blockIdx.x, tiles = P.tiles_x * P.tiles_y;
+  const int b = blockIdx.x, tiles = P.ftiles_x * P.ftiles_y;
   double acc[2] = {0.0, 0.0};
   for (int t = threadIdx.x; t < tiles; t += kThreads) {
     acc[0] += pe_part[((long long)b * tiles + t) * 2 + 0];
@@ -646,12 +612,26 @@ cudaError_t launch_forward(const KP& P, const FwdBuffers& Wk, float* loss, float
   return cudaGetLastError();
 }
 
-cudaError_t launch_consistency(const KP& P, double* stat_part, int stat_chunks, double* pe_part, float* ab, float* out,
-                               cudaStream_t st) {
-  k_warp_stats<1, false, false><<<dim3(stat_chunks, P.B), kThreads, 0, st>>>(P, stat_part, nullptr, nullptr, nullptr);
-  k_lcc_solve<<<P.B, 32, 0, st>>>(P, stat_part, stat_chunks, ab, nullptr);
-  k_consistency_pe<<<dim3(P.tiles_x, P.tiles_y, P.B), kThreads, 0, st>>>(P, ab, pe_part);
-  k_consistency_final<<<P.B, kThreads, 0, st>>>(P, pe_part, ab, out);
+cudaError_t launch_consistency(const KP& P0, double* stat_part, int stat_chunks, double* pe_part, float* ab, float* out,
+                               float4* iw, int pairs_per_pass, cudaStream_t st) {
+  // The warped frames go through a scratch buffer of `pairs_per_pass` frames: the sweep runs in passes of that many
+  // pairs (statistics + warp, (a, b), photometric error), each pass re-using the buffer.
+  const int tiles = P0.ftiles_x * P0.ftiles_y;
+  for (int p0 = 0; p0 < P0.B; p0 += pairs_per_pass) {
+    KP P = P0;
+    P.B = (P0.B - p0 < pairs_per_pass) ? P0.B - p0 : pairs_per_pass;
+    P.tgt = static_cast<const float*>(P0.tgt) + (long long)p0 * P0.tgt_bf * P0.frame_el;
+    P.srcs = static_cast<const float*>(P0.srcs) + (long long)p0 * P0.src_bf * P0.frame_el;
+    P.depth[0] = P0.depth[0] + (long long)p0 * P0.depth_bs[0];
+    P.K = P0.K + (long long)p0 * P0.K_bs;
+    P.T = P0.T + (long long)p0 * P0.T_bs;
+    double* sp = stat_part + (long long)p0 * stat_chunks * kStatVals;
+    float* abp = ab + 2 * p0;
+    k_warp_stats<1, false, false><<<dim3(stat_chunks, P.B), kThreads, 0, st>>>(P, sp, nullptr, iw, nullptr);
+    k_lcc_solve<<<P.B, 32, 0, st>>>(P, sp, stat_chunks, abp, nullptr);
+    k_consistency_pe<<<dim3(P.ftiles_x, P.ftiles_y, P.B), kFwdThreads, 0, st>>>(P, abp, iw, pe_part + (long long)p0 * tiles * 2);
+  }
+  k_consistency_final<<<P0.B, kThreads, 0, st>>>(P0, pe_part, ab, out);
   return cudaGetLastError();
 }
 

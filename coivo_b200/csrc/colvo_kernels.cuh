@@ -186,13 +186,8 @@ __device__ __forceinline__ void warp_sample(const KP& P, const Img<PK>& src, con
   for (int c = 0; c < 3; ++c) x[c] = bilerp(tx.i00[c], tx.i01[c], tx.i10[c], tx.i11[c], t.wx, t.wy);
 }
 
-// 4-byte asynchronous global->shared copy (LDGSTS); zero-fills the destination when !pred
-__device__ __forceinline__ void cp_async4(float* smem, const float* gmem, bool pred) {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  const int sz = pred ? 4 : 0;
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(sa), "l"(gmem), "r"(sz));
-}
-// 16-byte variant, L2-only (.cg): streaming data that should not displace the texels in L1
+// 16-byte asynchronous global->shared copy (LDGSTS), L2-only (.cg): streaming data that should not displace the
+// texels in L1; zero-fills the destination when !pred
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool pred) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
   const int sz = pred ? 16 : 0;
@@ -225,9 +220,6 @@ __device__ __forceinline__ void cp_async4_s(unsigned saddr, const void* gmem) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait_but() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void cp_async_wait_but_one() { cp_async_wait_but<1>(); }
 
 // bilinear sample of one extra plane (the source depth map) with the taps of a warped pixel
 __device__ __forceinline__ float sample_plane(const float* __restrict__ plane, const Taps& t, int W, float (&d)[4]) {
@@ -391,6 +383,6 @@ cudaError_t launch_backward(const KP& P, const BwdBuffers& W, const float* grad_
                             const SavedView& saved, float* const* grad_depth, float* grad_T, float* grad_srcs,
                             float* grad_src_depth, cudaStream_t st);
 cudaError_t launch_consistency(const KP& P, double* stat_part, int stat_chunks, double* pe_part, float* ab,
-                               float* out, cudaStream_t st);
+                               float* out, float4* iw, int pairs_per_pass, cudaStream_t st);
 
 }  // namespace colvo
