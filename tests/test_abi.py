@@ -72,3 +72,22 @@ def test_null_pointer_and_alignment_checks_without_touching_the_gpu():
     assert rc == -3
     assert lib.colvo_debug_time_kernel(7, None, None) == -5
     assert lib.colvo_debug_time_kernel(0, None, None) == 0
+
+
+def test_step_host_arena_gradient_offsets():
+    """colvo_step_host_arena_grads: byte offsets of the device-resident gradients inside the caller's arena --
+    16-byte aligned, disjoint, inside colvo_step_host_arena_bytes."""
+    lib = _lib.load()
+    d = _lib.make_desc(3, 2, 4, 64, 96, _lib.F_LCC)
+    total = ctypes.c_size_t()
+    assert lib.colvo_step_host_arena_bytes(ctypes.byref(d), ctypes.byref(total)) == 0
+    offs = (ctypes.c_size_t * _lib.MAX_SCALES)()
+    oT, oS = ctypes.c_size_t(), ctypes.c_size_t()
+    assert lib.colvo_step_host_arena_grads(ctypes.byref(d), offs, ctypes.byref(oT), ctypes.byref(oS)) == 0
+    spans = [(offs[k], 4 * 3 * (64 >> k) * (96 >> k)) for k in range(4)] + [(oT.value, 4 * 3 * 2 * 16), (oS.value, 4 * 3 * 2 * 3 * 64 * 96)]
+    for off, n in spans:
+        assert off % 16 == 0 and off + n <= total.value
+    spans.sort()
+    for (a, n), (b, _) in zip(spans, spans[1:]):
+        assert a + n <= b
+    assert lib.colvo_step_host_arena_grads(ctypes.byref(d), None, ctypes.byref(oT), ctypes.byref(oS)) == -3
