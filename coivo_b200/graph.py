@@ -1,8 +1,9 @@
 """CUDA-graph capture of one forward+backward step of the path.
 
 The C ABI only enqueues work on the caller's stream (no allocation, no synchronisation), so a
-whole `photometric_loss(...).backward()` step captures into one CUDA graph: ~10 kernel launches,
-a memset and the autograd bookkeeping collapse into a single `cudaGraphLaunch`.  Inputs are static
+whole `photometric_loss(...).backward()` step captures into one CUDA graph: nine kernel launches
+(with their programmatic-dependent-launch edges) and the autograd bookkeeping collapse into a single
+`cudaGraphLaunch`.  Inputs are static
 tensors: copy new data into them (`tensor.copy_`) between replays.
 """
 from __future__ import annotations
@@ -39,10 +40,11 @@ class GraphedStep:
             torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
         except AttributeError:
             pass
+        self._one = torch.ones((), dtype=torch.float32, device=dev)     # d loss / d loss, made once (no fill in the graph)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.loss = photometric_loss(self.depth, self.pose, self.K, self.tgt, self.srcs, **self.kw)
-            self.loss.backward()
+            self.loss.backward(gradient=self._one)
 
     def _eager(self):
         for t in self._leaves:

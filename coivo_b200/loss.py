@@ -146,6 +146,7 @@ class _PhotoLossFn(torch.autograd.Function):
             extra = (src_depth,) if src_depth is not None else ()
             ctx.save_for_backward(pose, K, tgt, srcs, sel, saved, *extra, *depth)
         ctx.mark_non_differentiable(ab, sel)
+        ctx.set_materialize_grads(False)      # no zero-filled "gradients" for the mask outputs (a 4 MB fill per step)
         if valid is not None:
             ctx.mark_non_differentiable(valid)
             return loss, ab, sel, valid
@@ -153,6 +154,8 @@ class _PhotoLossFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_loss, *unused):
+        if grad_loss is None:                 # the loss itself was not used
+            return (None,) * (11 + ctx.n_depth)
         pose, K, tgt, srcs, sel, saved = ctx.saved_tensors[:6]
         src_depth = ctx.saved_tensors[6] if ctx.has_src_depth else None
         depth = ctx.saved_tensors[7:] if ctx.has_src_depth else ctx.saved_tensors[6:]
