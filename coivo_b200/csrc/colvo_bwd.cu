@@ -1,15 +1,19 @@
 // Backward kernels of the ColVO photometric-loss path (SURVEY.md section 8(a) row 11 and
 // appendix A), hand-written for sm_100a.  The adjoint is analytic (no tape): the forward
-// saves only sel, (a, b), the LCC statistics, dL/da, dL/db and the smoothness adjoint field;
-// everything else is recomputed.
+// saves sel, (a, b), the LCC statistics, dL/da, dL/db, the smoothness adjoint field, the SSIM
+// adjoint coefficients of the winning candidate and the projection (u', v', iz, D^) of every pixel.
 //
-//   k_photo_bwd      per 32x8 tile: re-warp of the own pixel, SSIM adjoint gathered from the
-//                    coefficient fields the forward saved, LCC adjoint, bilinear scatter-add
-//                    (REDG) into grad_srcs, projection adjoint -> full-resolution depth adjoint
-//                    + per-tile pose-gradient partials; scale 0 also gets its smoothness gradient
-//   k_depth_gather   adjoint of the bilinear depth up-sample in gather form (no atomics),
-//                    plus the smoothness gradient of scales k >= 1
-//   k_pose_final     deterministic reduction of the pose-gradient partials
+//   k_zero           zero-fill of the scatter accumulators (a kernel, so the next one can be launched behind it
+//                    programmatically)
+//   k_photo_bwd      per 32 x kBwdTileH tile: SSIM adjoint gathered from the saved coefficient fields (tiles staged
+//                    by cp.async + mbarriers), four taps per source at the saved coordinates, LCC adjoint,
+//                    bilinear scatter-add as one vector RED per tap into a texel-interleaved accumulator,
+//                    projection adjoint -> full-resolution depth adjoint + per-tile pose-gradient partials;
+//                    scale 0 also gets its smoothness gradient
+//   k_depth_gather   adjoint of the bilinear depth up-sample in gather form (no atomics) plus the smoothness
+//                    gradient of scales k >= 1; its extra grid rows do the deterministic pose reduction
+//                    (pose_final_block) and unpack the source-gradient texels into the planar grad_srcs
+//   k_pose_final     the same epilogue blocks on their own when S = 1
 #include "colvo_kernels.cuh"
 
 #ifndef COLVO_BWD_L2_HINT    // 1: load the saved coefficients / projections (each read once) with L2 evict-first priority (measured: no effect)
@@ -42,7 +46,7 @@ __device__ __forceinline__ float smooth_grad(float s, float D, float inv, float 
   return -(s * inv - corr) * dr * dr;
 }
 
-// One CTA = one 32x8 tile of one triplet.  The SSIM adjoint coefficients of every window were
+// One CTA = one 32 x kBwdTileH (8) tile of one triplet.  The SSIM adjoint coefficients of every window were
 // written by the forward (for the winning candidate, zeros where an identity candidate won; .w = index
 // of the winning source), and k_warp_stats saved the projection (u', v', iz, D^|valid) of every pixel,
 // so the tile needs neither a halo re-warp nor a re-projection: per scale the CTA stages the

@@ -5,8 +5,8 @@
 //                   shared memory, loss partials, adjoint field when saving              (row 9)
 //   k_warp_stats    warp every (b,n,k) frame once, fp64 LCC sums, valid mask          (rows 0-5)
 //   k_lcc_solve     (a, b) per warped frame                                           (row 5)
-//   k_photo_fwd     per 32x8 tile: identity + re-projection candidates, SSIM+L1,
-//                   min-reprojection / auto-mask, loss partials, dL/da, dL/db         (rows 0-8)
+//   k_photo_fwd     (colvo_photo_fwd.cuh) per 32x12 tile, strip walk: identity + re-projection candidates,
+//                   SSIM+L1, min-reprojection / auto-mask, loss partials, dL/da, dL/db  (rows 6-8)
 //   k_finalize_fwd  deterministic final sums -> loss, G_a, G_b, sum s*d               (row 10)
 #include "colvo_kernels.cuh"
 #include "colvo_photo_fwd.cuh"

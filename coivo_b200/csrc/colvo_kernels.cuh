@@ -67,7 +67,7 @@ struct KP {
   int K_bs, T_bs, T_ns;
   int tiles_x, tiles_y;               // 32 x 8 tiles (consistency sweep; sizing of the forward partials)
   int btiles_y;                       // rows of 32 x kBwdTileH tiles of the backward kernel
-  int ftiles_x, ftiles_y;             // 32 x 16 tiles of the forward kernel
+  int ftiles_x, ftiles_y;             // 32 x kFwdTileH tiles of the forward kernel
 };
 
 __device__ __forceinline__ Cam load_cam(const KP& P, int b) {
