@@ -239,9 +239,11 @@ class HostStepper:
     and reads back the loss only -- `device_grads()` returns views of them."""
 
     def __init__(self, B, N, S, H, W, *, device="cuda:0", lcc=True, lcc_detach=False, want_src_grad=True,
-                 alpha=0.85, smooth_weight=1e-3, chunks=3, grads="host"):
+                 alpha=0.85, smooth_weight=1e-3, chunks=None, grads="host"):
         if grads not in ("host", "device"):
             raise ValueError("grads must be 'host' or 'device'")
+        if chunks is None:       # measured on B200 / PCIe 5 (scripts/e2e_chunks.py): two streams keep the H2D engine busy
+            chunks = 3 if grads == "host" else 2     # when only the loss comes back, three also overlap the gradient D2H
         self.grads = grads
         self.N, self.H, self.W = N, H, W
         self.lib = _lib.load()
