@@ -35,27 +35,55 @@ for case in range(n_cases):
     if rng.random() < 0.3: kw["alpha"] = rng.choice([0.5, 0.7, 1.0])
     if rng.random() < 0.3: kw["smooth_weight"] = rng.choice([0.0, 1e-2, 0.1])
     d = make_triplets(B, H, W, N=N, S=S, seed=1000 + case)
+    variant = rng.random()
+    if variant < 0.2:            # packed bf16 image storage (f-3): the oracle sees the same quantised values; no source gradient
+        tp, sp = coivo_b200.pack_images(d["tgt"]), coivo_b200.pack_images(d["srcs"])
+        d["tgt"], d["srcs"] = coivo_b200.unpack_images(tp), coivo_b200.unpack_images(sp)
+        kw_tag = dict(kw, packed=True)
+    elif variant < 0.4:          # geometric-consistency term (f-2)
+        g = torch.Generator().manual_seed(case)
+        sd = (1.0 + 0.5 * torch.rand(B, N, 1, H, W, generator=g)).contiguous()
+        kw_tag = dict(kw, geo=True)
+    else:
+        kw_tag = kw
     depth = [x.to(DEV).requires_grad_() for x in d["depth"]]
-    pose = d["pose"].to(DEV).requires_grad_(); srcs = d["srcs"].to(DEV).requires_grad_()
-    loss, valid, sel, ab = coivo_b200.photometric_loss(depth, pose, d["K"].to(DEV), d["tgt"].to(DEV), srcs, return_masks=True, **kw)
+    pose = d["pose"].to(DEV).requires_grad_()
+    okw = dict(kw)
+    if variant < 0.2:
+        srcs = None
+        loss, valid, sel, ab = coivo_b200.photometric_loss(depth, pose, d["K"].to(DEV), tp.to(DEV), sp.to(DEV), return_masks=True, **kw)
+    else:
+        srcs = d["srcs"].to(DEV).requires_grad_()
+        if 0.2 <= variant < 0.4:
+            sdg = sd.to(DEV).requires_grad_()
+            kw = dict(kw, src_depth=sdg, geo_weight=0.5)
+            osd = sd.clone().requires_grad_()
+            okw = dict(okw, src_depth=osd, geo_weight=0.5)
+        loss, valid, sel, ab = coivo_b200.photometric_loss(depth, pose, d["K"].to(DEV), d["tgt"].to(DEV), srcs, return_masks=True, **kw)
     loss.backward(); torch.cuda.synchronize()
+    kw = {k: v for k, v in okw.items() if k not in ("src_depth", "geo_weight")}
     with torch.no_grad():
         l0, v0, s0, ab0 = O.photometric_loss(d["depth"], d["pose"], d["K"], d["tgt"], d["srcs"], return_masks=True, **kw)
         gap = O.candidate_gap(d["depth"], d["pose"], d["K"], d["tgt"], d["srcs"], alpha=kw.get("alpha", 0.85), lcc=kw.get("lcc", True))
     od = [x.clone().requires_grad_() for x in d["depth"]]; op = d["pose"].clone().requires_grad_(); osr = d["srcs"].clone().requires_grad_()
-    O.photometric_loss(od, op, d["K"], d["tgt"], osr, sel_override=sel.cpu(), ab_override=ab.cpu(), **kw).backward()
+    lref = O.photometric_loss(od, op, d["K"], d["tgt"], osr, sel_override=sel.cpu(), ab_override=ab.cpu(), **okw)
+    lref.backward()
     kinks = O.l1_kink_count(d["depth"], d["pose"], d["K"], d["tgt"], d["srcs"], sel.cpu(), ab.cpu()) if kw.get("alpha", 0.85) < 1 else 0
     mism = sel.cpu() != s0
-    ok = torch.equal(valid.cpu(), v0) and bool((gap[mism] < 1e-4).all()) and abs(loss.item() - l0.item()) <= TOL * abs(l0.item())
+    lcmp = lref if "geo_weight" in okw else l0      # (the geometric term: loss compared with the kernel's own sel / ab)
+    ok = torch.equal(valid.cpu(), v0) and bool((gap[mism] < 1e-4).all()) and abs(loss.item() - lcmp.item()) <= TOL * abs(lcmp.item())
     ok = ok and torch.allclose(ab.cpu(), ab0, rtol=1e-5, atol=1e-6)
     worst = 0.0
     for k in range(S):
         c, e = close(depth[k].grad.cpu(), od[k].grad, kinks, atol=1e-12); ok = ok and c; worst = max(worst, e)
     gp = op.grad[:, :, :3]
     e = (pose.grad.cpu()[:, :, :3] - gp).abs().max().item() / max(gp.abs().max().item(), 1e-30); ok = ok and e < TOL; worst = max(worst, e)
-    c, e = close(srcs.grad.cpu(), osr.grad, kinks); ok = ok and c; worst = max(worst, e)
+    if srcs is not None:
+        c, e = close(srcs.grad.cpu(), osr.grad, kinks); ok = ok and c; worst = max(worst, e)
+    if "geo_weight" in okw:
+        c, e = close(sdg.grad.cpu(), osd.grad, kinks); ok = ok and c; worst = max(worst, e)
     note = ""
-    if not ok:
+    if not ok and srcs is not None and "geo_weight" not in okw:
         # ill-conditioned (degenerate) shapes: the fp32 oracle itself may sit further from an fp64 evaluation than the
         # tolerance; then the kernel is judged against the fp64 oracle (same sel / ab protocol)
         d64 = [x.double().clone().requires_grad_() for x in d["depth"]]; p64 = d["pose"].double().clone().requires_grad_()
@@ -67,7 +95,7 @@ for case in range(n_cases):
         f32_vs_f64 = (osr.grad.double() - s64.grad).abs().max().item() / max(s64.grad.abs().max().item(), 1e-30)
         if ok64 and e64 < TOL and torch.equal(valid.cpu(), v0) and abs(loss.item() - l0.item()) <= TOL * abs(l0.item()):
             ok, note = True, f" [within 1e-4 of the fp64 oracle; fp32 oracle vs fp64: {f32_vs_f64:.1e}]"
-    print(f"{'ok ' if ok else 'BAD'} B={B} {H}x{W} N={N} S={S} {kw} kinks={kinks} sel_mism={int(mism.sum())} worst_rel={worst:.2e}{note}", flush=True)
+    print(f"{'ok ' if ok else 'BAD'} B={B} {H}x{W} N={N} S={S} {kw_tag} kinks={kinks} sel_mism={int(mism.sum())} worst_rel={worst:.2e}{note}", flush=True)
     bad += 0 if ok else 1
 print(f"{n_cases - bad}/{n_cases} cases within tolerance")
 sys.exit(1 if bad else 0)
