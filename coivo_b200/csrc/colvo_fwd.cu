@@ -141,7 +141,9 @@ __global__ void __launch_bounds__(kThreads)
     float* sf = O.sf[k] ? O.sf[k] + (long long)b * hk * wk : nullptr;
     const float cx = P.sm_cx[k], cy = P.sm_cy[k];
     float acc[kSmVals] = {0.f, 0.f, 0.f, 0.f};      // at most 8 texels per thread and scale: fp32, then fp64 across threads
-    const int tw_log = 6 - k;                       // tw = kSmBW >> k is a power of two
+    constexpr int kSmBWLog = (kSmBW == 128) ? 7 : (kSmBW == 64 ? 6 : (kSmBW == 32 ? 5 : (kSmBW == 16 ? 4 : 3)));
+    static_assert((1 << kSmBWLog) == kSmBW, "kSmBW must be a power of two in [8, 128]");
+    const int tw_log = kSmBWLog - k;                // tw = kSmBW >> k is a power of two
     for (int i = tid; i < tw * th; i += kThreads) {
       const int ly = i >> tw_log, lx = i & (tw - 1);
       const int gy = (Y0 >> k) + ly, gx = (X0 >> k) + lx;

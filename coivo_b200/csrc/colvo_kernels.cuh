@@ -31,7 +31,13 @@ constexpr int kFwdTileH = kFwdWarps * kFwdRows;   // 12
 #endif
 constexpr int kStatPPT = COLVO_STAT_PPT;   // pixels per thread in the LCC statistics pass
 constexpr int kStatVals = 6;     // per (frame, chunk): n, Sx, Sy, Sxx, Sxy, sum of geometric-consistency diffs
-constexpr int kSmBW = 64, kSmBH = 16; // full-resolution pixels per smoothness block (k_smooth)
+#ifndef COLVO_SM_BW
+#define COLVO_SM_BW 64
+#endif
+#ifndef COLVO_SM_BH
+#define COLVO_SM_BH 16
+#endif
+constexpr int kSmBW = COLVO_SM_BW, kSmBH = COLVO_SM_BH;   // full-resolution pixels per smoothness block (k_smooth); powers of two >= 8
 constexpr int kSmVals = 4;            // per block and scale: sum over x edges, sum over y edges, sum s*d, sum d
 
 // saved[] layout: doubles  [B*N*S][kSavedPerFrame]  n, mean_x, mean_y, 1/(n (var+eps)), a, b, G_a, G_b

@@ -5,9 +5,10 @@ from coivo_b200 import _lib
 
 VARIANTS = {
     "base": [],
-    "t4": ["COLVO_BWD_TILE_H=4"],
-    "t6": ["COLVO_BWD_TILE_H=6"],
-    "t2": ["COLVO_BWD_TILE_H=2"],
+    "sm32x16": ["COLVO_SM_BW=32"],
+    "sm64x8": ["COLVO_SM_BH=8"],
+    "sm128x8": ["COLVO_SM_BW=128", "COLVO_SM_BH=8"],
+    "sm32x32": ["COLVO_SM_BW=32", "COLVO_SM_BH=32"],
 }
 out = os.path.join(os.path.dirname(_lib.PKG_DIR), "build", "variants")
 os.makedirs(out, exist_ok=True)
