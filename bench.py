@@ -266,6 +266,25 @@ def run_ours(args):
     clocks = sampler.stop() if sampler else None
     e2e_ms, e2e_full_ms = e2e["device"]["ms"], e2e["host"]["ms"]
 
+    # Reported separately (assumption A13): the training loop's gradient all-reduce of the
+    # out-of-scope depth / pose CNNs (~28 M fp32 parameters) over NCCL / NVLink -- not part of the path or of `value`.
+    ddp = None
+    if world > 1:
+        gbuf = torch.zeros(28_000_000, dtype=torch.float32, device=dev)
+        for _ in range(3):
+            dist.all_reduce(gbuf)
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(10):
+            dist.all_reduce(gbuf)
+        a1.record()
+        barrier()
+        tt = torch.tensor([a0.elapsed_time(a1) / 10], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ddp = {"bytes": gbuf.numel() * 4, "ms": tt.item(), "note": "dummy 28 M-parameter fp32 gradient all-reduce (NCCL), timed on its own"}
+        del gbuf
+
     t = torch.tensor([ms_total, e2e_ms, kern_ms, graph_ms if graph_ms is not None else 0.0, e2e_full_ms], dtype=torch.float64,
                      device=dev)
     if world > 1:
@@ -297,7 +316,7 @@ def run_ours(args):
                        "frames_per_triplet": "1 target + 2 sources; frames/s counts target frames (= triplets/s)",
                        "launch": launch, "eager_ms_per_step": eager_ms / steps,
                        "graph_ms_per_step": (graph_ms_max / steps) if graph_ms is not None else None,
-                       "eager_wall_ms_per_step": t_wall / steps * 1e3},
+                       "eager_wall_ms_per_step": t_wall / steps * 1e3, "ddp_dummy_allreduce": ddp},
             "roofline": {"bound": "hbm", "kernel": "k_photo_bwd", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": kern_bytes, "kernel_ms": kern_ms,
