@@ -1,6 +1,6 @@
 """Diagnostic run on a B200: prints parity errors (does not assert) and a rough timing."""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import coivo_b200
 from coivo_b200.synthetic import make_triplets

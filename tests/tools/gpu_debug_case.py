@@ -1,6 +1,6 @@
 """Diagnostic: where does grad_depth differ from the oracle for one case?  (B200 only; prints, does not assert)"""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import coivo_b200
 from coivo_b200.synthetic import make_triplets

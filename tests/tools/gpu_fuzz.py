@@ -2,7 +2,7 @@
 summary; exits non-zero on a parity violation).  Covers ragged and tiny shapes, exact and inexact pyramid ratios,
 N in {1,2}, S in 1..4, lcc / lcc_detach / alpha / smooth_weight variations."""
 import os, random, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import coivo_b200
 from coivo_b200.synthetic import make_triplets
