@@ -35,7 +35,7 @@ int check_desc(const ColvoDesc* d) {
   if (d->B < 1 || d->N < 1 || d->N > COLVO_MAX_SOURCES || d->S < 1 || d->S > COLVO_MAX_SCALES) return COLVO_E_BAD_DESC;
   if (d->H < 2 || d->W < 2) return COLVO_E_BAD_DESC;
   if ((long long)d->H * d->W > (1ll << 26)) return COLVO_E_BAD_DESC;   // 9 * HW element offsets stay 32-bit
-  if (d->B > 65535) return COLVO_E_BAD_DESC;
+  if (d->B > 65535 || (long long)d->B * d->S > 65535) return COLVO_E_BAD_DESC;   // (b, k) pairs ride on grid.y
   for (int k = 0; k < d->S; ++k) {
     if (d->h[k] != (d->H >> k) || d->w[k] != (d->W >> k)) return COLVO_E_BAD_DESC;
     if (d->h[k] < 1 || d->w[k] < 1) return COLVO_E_BAD_DESC;
@@ -374,6 +374,8 @@ int colvo_photo_step_host(const ColvoDesc* d_in, const float* h_tgt, const float
   d.flags |= COLVO_F_SAVE_FOR_BWD;
   const bool want_src = !(d.flags & COLVO_F_NO_SRC_GRAD);
   if (grads_to_host && want_src && !h_grad_srcs) return COLVO_E_NULL_PTR;
+  for (int k = 0; k < d.S; ++k)              // every pointer is checked before the first copy is enqueued
+    if (!h_depth[k] || (grads_to_host && !h_grad_depth[k])) return COLVO_E_NULL_PTR;
   if ((uintptr_t)arena & 255u) return COLVO_E_MISALIGNED;
   Arena A;
   if (carve_arena(&d, arena, A) > arena_bytes) return COLVO_E_WORKSPACE;
@@ -387,10 +389,7 @@ int colvo_photo_step_host(const ColvoDesc* d_in, const float* h_tgt, const float
   } while (0)
   CV_COPY(A.tgt, h_tgt, B * 3 * HW, cudaMemcpyHostToDevice);
   CV_COPY(A.srcs, h_srcs, B * N * 3 * HW, cudaMemcpyHostToDevice);
-  for (int k = 0; k < d.S; ++k) {
-    if (!h_depth[k] || (grads_to_host && !h_grad_depth[k])) return COLVO_E_NULL_PTR;
-    CV_COPY(A.depth[k], h_depth[k], B * d.h[k] * d.w[k], cudaMemcpyHostToDevice);
-  }
+  for (int k = 0; k < d.S; ++k) CV_COPY(A.depth[k], h_depth[k], B * d.h[k] * d.w[k], cudaMemcpyHostToDevice);
   CV_COPY(A.K, h_K, B * 9, cudaMemcpyHostToDevice);
   CV_COPY(A.T, h_T, B * N * 16, cudaMemcpyHostToDevice);
   k_fill_scalar<<<1, 1, 0, st>>>(A.one, grad_scale);

@@ -16,23 +16,27 @@
 //   k_pose_final     the same epilogue blocks on their own when S = 1
 #include "colvo_kernels.cuh"
 
-#ifndef COLVO_BWD_L2_HINT    // 1: load the saved coefficients / projections (each read once) with L2 evict-first priority (measured: no effect)
-#define COLVO_BWD_L2_HINT 0
-#endif
-#ifndef COLVO_BWD_PIPE       // 1: software pipeline of the per-scale loads: the saved projection of scale k+1 is fetched during
-#define COLVO_BWD_PIPE 0     //    scale k, and the taps of scale k are issued BEFORE its coefficient gather (more registers)
-#endif
-#ifndef COLVO_EXP_NOBAR      // timing experiments only (wrong results)
-#define COLVO_EXP_NOBAR 0
-#endif
+// Ablation builds for the timing experiments logged under profiles/ (scripts/build_variants.py): they skip the
+// coefficient gather / the scatter and therefore give WRONG gradients; the package never loads such a build.
 #ifndef COLVO_EXP_NOGATHER
 #define COLVO_EXP_NOGATHER 0
 #endif
 #ifndef COLVO_EXP_NORED
 #define COLVO_EXP_NORED 0
 #endif
+#ifndef COLVO_BWD_CHAIN_PACKED   // 1: the per-source chain of k_photo_bwd runs both sources in packed fp32x2 lanes (fewer issue
+#define COLVO_BWD_CHAIN_PACKED 1 //    slots, ~127 registers); 0: one source after the other (the gather stays packed either way)
+#endif
 #ifndef COLVO_MINB_BWD      // CTAs per SM the register allocator must allow -- tuned on B200, see DESIGN.md
 #define COLVO_MINB_BWD (24 / COLVO_BWD_TILE_H)     // 24 warps per SM at 80 registers
+#endif
+
+#ifdef COLVO_DEBUG_DUMP     // diagnostic builds only (tests/tools): per-pixel internals of k_photo_bwd at k = 0, source 0
+__device__ float* g_colvo_dbg = nullptr;
+extern "C" int colvo_debug_set_buffer(void* p) {
+  float* q = static_cast<float*>(p);
+  return (int)cudaMemcpyToSymbol(g_colvo_dbg, &q, sizeof(q));
+}
 #endif
 
 namespace colvo {
@@ -47,17 +51,23 @@ __device__ __forceinline__ float smooth_grad(float s, float D, float inv, float 
 }
 
 // One CTA = one 32 x kBwdTileH (8) tile of one triplet.  The SSIM adjoint coefficients of every window were
-// written by the forward (for the winning candidate, zeros where an identity candidate won; .w = index
-// of the winning source), and k_warp_stats saved the projection (u', v', iz, D^|valid) of every pixel,
-// so the tile needs neither a halo re-warp nor a re-projection: per scale the CTA stages the
-// coefficient tile (+1 halo) in shared memory, every thread gathers its 3x3 neighbourhood, samples
-// the four taps of each source at the saved coordinates, and pushes the result through the LCC,
-// bilinear and projection adjoints.
-struct BwdConst {          // per warped frame (n, k), built once per CTA
-  float a, b;              // LCC gain / bias
-  float l0, ly, lx;        // LCC adjoint of a valid sample: l0 + ly * y + lx * x
-  float wl1;               // weight of the L1 term's sign at the own pixel: wscale * (1 - alpha) / 3 * a
-  float pad0, pad1;
+// written by the forward (for the winning candidate; the winner flags ride in .w of channels 0 / 1), and
+// k_warp_stats saved the projection (u', v', iz, D^, valid) of every pixel, so the tile needs neither a halo
+// re-warp nor a re-projection: per scale the CTA stages the coefficient tile (+1 halo) in shared memory, every
+// thread gathers its 3x3 neighbourhood, samples the four taps of each source at the saved coordinates, and
+// pushes the result through the LCC, bilinear and projection adjoints.
+//
+// Blackwell specifics: with N = 2 the two sources ride in the two lanes of packed fp32x2 registers (colvo_f2.cuh)
+// from the gather (one FFMA2 per coefficient feeds both sources' accumulators: the lane weights are the window's
+// winner flags) through the bilinear / LCC / projection adjoints and the pose sums; only the tap addressing and
+// the scatter products stay per source.  The saved projection is stored lane-interleaved for that:
+//   N = 1:  geo[(b,k)][pix]  = (u', v', iz, D^ | valid in the mantissa LSB)
+//   N = 2:  geoA[(b,k)][pix] = (u'^0, u'^1, v'^0, v'^1),  geoB[(b,k)][pix] = (iz^0, iz^1, D^, valid bits)
+template <int NS>
+struct BwdConstV {         // per scale, lane n = warped frame (n, k); built once per CTA
+  Vn<NS> a, b;             // LCC gain / bias
+  Vn<NS> l0, ly, lx;       // LCC adjoint of a valid sample: l0 + ly * y + lx * x
+  Vn<NS> wl1;              // weight of the L1 term's sign at the own pixel: wscale * (1 - alpha) / 3 * a
 };
 
 template <int NS, bool GEO, bool PK>
@@ -68,17 +78,19 @@ __global__ void __launch_bounds__(kBwdThreads, COLVO_MINB_BWD)
                 const float4* __restrict__ geo_in, float* __restrict__ grad_d0,
                 float* __restrict__ dD1, float* __restrict__ dD2, float* __restrict__ dD3,
                 float4* __restrict__ gsrc4, float* __restrict__ grad_src_depth, double* __restrict__ pose_part) {
+  typedef Vn<NS> V;
   // dynamic shared memory, carved by hand
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float4 (*coef)[kCN * 3] = reinterpret_cast<float4 (*)[kCN * 3]>(smem_raw);   // [2]: (ca, cb, cg, n) per window
+  float4 (*coef)[kCN * 3] = reinterpret_cast<float4 (*)[kCN * 3]>(smem_raw);   // [2]: (ca, cb, cg, flag) per window
                                                                                // centre and channel, double-buffered over k
   double* red = reinterpret_cast<double*>(smem_raw + sizeof(float4) * 2 * kCN * 3);
-  BwdConst (*cst)[kMaxS] = reinterpret_cast<BwdConst (*)[kMaxS]>(red + (kBwdThreads / 32) * NS * 12);   // [NS][kMaxS]
-  float (*pose_s)[12] = reinterpret_cast<float (*)[12]>(cst + NS);                                   // [NS]: R row-major, t
-  float* cst_sm = reinterpret_cast<float*>(pose_s + NS);   // scale 0: 1/(mean+eps), sum(s d)/(n (mean+eps)^2)
+  BwdConstV<NS>* cst = reinterpret_cast<BwdConstV<NS>*>(red + (kBwdThreads / 32) * NS * 12);    // [kMaxS]
+  V* pose_s = reinterpret_cast<V*>(cst + kMaxS);                                            // [12]: R row-major, t; lane n
+  float* cst_sm = reinterpret_cast<float*>(pose_s + 12);   // scale 0: 1/(mean+eps), sum(s d)/(n (mean+eps)^2)
   // full[i]: the copies into coefficient buffer i have landed (cp.async arrivals); empty[i]: every thread is done reading it
   unsigned long long* mbar = reinterpret_cast<unsigned long long*>(smem_raw + sizeof(float4) * 2 * kCN * 3 +
                                                                    sizeof(double) * (kBwdThreads / 32) * NS * 12 + 1024);
+  static_assert(sizeof(BwdConstV<NS>) * kMaxS + sizeof(V) * 12 + 2 * sizeof(float) <= 1024, "constant area");
 
   pdl_trigger();         // the epilogue launch may become resident while this kernel drains
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
@@ -95,29 +107,29 @@ __global__ void __launch_bounds__(kBwdThreads, COLVO_MINB_BWD)
   // ---- phase 0: per-frame constants ----
   if (tid < NS * kMaxS) {
     const int n = tid / kMaxS, k = tid % kMaxS;
-    BwdConst c;
-    c.a = 1.f; c.b = 0.f; c.l0 = c.ly = c.lx = 0.f; c.pad0 = c.pad1 = 0.f;
+    float ca = 1.f, cb = 0.f, l0 = 0.f, ly = 0.f, lx = 0.f;
     if (k < P.S) {
       const double* s = saved_frame + ((long long)(b * P.N + n) * P.S + k) * kSavedPerFrame;
-      c.a = (float)s[4];
-      c.b = (float)s[5];
+      ca = (float)s[4];
+      cb = (float)s[5];
       if ((P.flags & 1u) && !(P.flags & 2u) && s[0] > 0.0) {
         // lcc_q = Pc * ((y - my) - 2 a (x - mx)) - Qc   (SURVEY.md appendix A), expanded in y and x
         const double Pc = (double)go * (s[6] - s[7] * s[1]) * s[3];
         const double Qc = (double)go * s[7] * s[4] / s[0];
         const double a = s[4];
-        c.ly = (float)Pc;
-        c.lx = (float)(-2.0 * a * Pc);
-        c.l0 = (float)(-Pc * s[2] + 2.0 * a * Pc * s[1] - Qc);
+        ly = (float)Pc;
+        lx = (float)(-2.0 * a * Pc);
+        l0 = (float)(-Pc * s[2] + 2.0 * a * Pc * s[1] - Qc);
       }
     }
-    c.wl1 = wscale * (1.f - P.alpha) * (1.0f / 3.0f) * c.a;
-    cst[n][k] = c;
+    BwdConstV<NS>& c = cst[k];
+    c.a.set(n, ca); c.b.set(n, cb); c.l0.set(n, l0); c.ly.set(n, ly); c.lx.set(n, lx);
+    c.wl1.set(n, wscale * (1.f - P.alpha) * (1.0f / 3.0f) * ca);
   }
   if (tid >= 32 && tid < 32 + NS * 12) {
     const int n = (tid - 32) / 12, j = (tid - 32) % 12;
     const float* t = P.T + (long long)b * P.T_bs + (long long)n * P.T_ns;
-    pose_s[n][j] = (j < 9) ? __ldg(t + 4 * (j / 3) + (j % 3)) : __ldg(t + 4 * (j - 9) + 3);
+    pose_s[j].set(n, (j < 9) ? __ldg(t + 4 * (j / 3) + (j % 3)) : __ldg(t + 4 * (j - 9) + 3));
   }
   if (tid == kBwdThreads - 1) {
     const double* sc = saved_scale + (long long)(b * P.S) * kSavedPerScale;
@@ -139,17 +151,12 @@ __global__ void __launch_bounds__(kBwdThreads, COLVO_MINB_BWD)
   const int oc = ty * kCW + tx;
 
   // pose gradient: per source only sum dXp_i * D and sum dXp_i are carried (see project_adjoint)
-  float pw[NS][3], pt[NS][3];
+  V pw[3], pt[3];
 #pragma unroll
-  for (int n = 0; n < NS; ++n)
-#pragma unroll
-    for (int i = 0; i < 3; ++i) pw[n][i] = pt[n][i] = 0.f;
+  for (int i = 0; i < 3; ++i) pw[i] = pt[i] = bc<NS>(0.f);
 
   // Coefficient tile of scale k (+1 halo; zeros outside the image), fetched with cp.async one scale ahead so its
   // global latency hides behind the previous scale's arithmetic.
-#if COLVO_BWD_L2_HINT
-  const unsigned long long l2pol = l2_evict_first_policy();
-#endif
   auto stage_coef = [&](int k) {
     float4* cbf = coef[k & 1];
     const float4* cin = reinterpret_cast<const float4*>(coef_in) + (long long)(b * P.S + k) * P.HW * 3;
@@ -159,13 +166,7 @@ __global__ void __launch_bounds__(kBwdThreads, COLVO_MINB_BWD)
       const bool on = gy >= 0 && gy < P.H && gx >= 0 && gx < P.W;
       const float4* p = on ? cin + (gy * P.W + gx) : cin;
 #pragma unroll
-      for (int ch = 0; ch < 3; ++ch) {
-#if COLVO_BWD_L2_HINT
-        cp_async16_hint(cbf + idx * 3 + ch, p + (long long)ch * P.HW, on, l2pol);
-#else
-        cp_async16(cbf + idx * 3 + ch, p + (long long)ch * P.HW, on);
-#endif
-      }
+      for (int ch = 0; ch < 3; ++ch) cp_async16(cbf + idx * 3 + ch, p + (long long)ch * P.HW, on);
     }
     mbar_arrive_cp_async(&mbar[k & 1]);      // this thread's share of full[k & 1]
   };
@@ -180,47 +181,28 @@ __global__ void __launch_bounds__(kBwdThreads, COLVO_MINB_BWD)
   // Everything above reads only what the forward saved.  Launched programmatically behind k_zero, the scatter targets
   // are guaranteed to be zero from here on.
   pdl_wait();
-#if COLVO_BWD_PIPE
-  float4 gt_next[NS];
-#pragma unroll
-  for (int n = 0; n < NS; ++n) gt_next[n] = __ldg(geo_in + (long long)((b * P.N + n) * P.S) * P.HW + qo);
-  int sel_next = __ldg(sel + ((long long)b * P.S) * P.HW + qo);
-#endif
 #pragma unroll 1
   for (int k = 0; k < P.S; ++k) {
     const float4* cb = coef[k & 1];
-    // projection of the own pixel into both sources, and which candidate won here
-    float4 gt[NS];
-#if COLVO_BWD_PIPE
-#pragma unroll
-    for (int n = 0; n < NS; ++n) gt[n] = gt_next[n];
-    const int own_sel = sel_next;
-    if (k + 1 < P.S) {
-#pragma unroll
-      for (int n = 0; n < NS; ++n) gt_next[n] = __ldg(geo_in + (long long)((b * P.N + n) * P.S + k + 1) * P.HW + qo);
-      sel_next = __ldg(sel + ((long long)b * P.S + k + 1) * P.HW + qo);
-    }
-    // taps and texels of both sources now, so that their latency hides behind the coefficient gather
-    Taps tp[NS];
-    Texels tq[NS];
-#pragma unroll
-    for (int n = 0; n < NS; ++n) {
-      const Img<PK> src = img_at<PK>(P, P.srcs, b * P.src_bf + n * P.src_nf);
-      tp[n] = make_taps(gt[n].x, gt[n].y, P.W, P.H);
-      const int r0 = tp[n].y0 * P.W, r1 = tp[n].y1 * P.W;
-      src.load_taps(r0 + tp[n].x0, r0 + tp[n].x1, r1 + tp[n].x0, r1 + tp[n].x1, tq[n]);
-    }
-#else
-#pragma unroll
-    for (int n = 0; n < NS; ++n) {
-#if COLVO_BWD_L2_HINT
-      gt[n] = ldg_f4_hint(geo_in + (long long)((b * P.N + n) * P.S + k) * P.HW + qo, l2pol);
-#else
-      gt[n] = __ldg(geo_in + (long long)((b * P.N + n) * P.S + k) * P.HW + qo);
-#endif
+    // projection of the own pixel into every source, and which candidate won here
+    V gu, gv, giz;
+    float D_own;
+    bool gvalid[NS];
+    if constexpr (NS == 1) {
+      const float4 g4 = __ldg(geo_in + (long long)(b * P.S + k) * P.HW + qo);
+      gu = V(g4.x); gv = V(g4.y); giz = V(g4.z);
+      D_own = g4.w;
+      gvalid[0] = (__float_as_uint(g4.w) & 1u) != 0u;
+    } else {
+      const float4 ga4 = __ldg(geo_in + (long long)(b * P.S + k) * P.HW + qo);
+      const float4 gb4 = __ldg(geo_in + (long long)((P.B + b) * P.S + k) * P.HW + qo);
+      gu = V(ga4.x, ga4.y); gv = V(ga4.z, ga4.w); giz = V(gb4.x, gb4.y);
+      D_own = gb4.z;
+      const unsigned vb = __float_as_uint(gb4.w);
+      gvalid[0] = (vb & 1u) != 0u;
+      gvalid[NS - 1] = (vb & 2u) != 0u;
     }
     const int own_sel = __ldg(sel + ((long long)b * P.S + k) * P.HW + qo);
-#endif
     // Two transaction barriers per buffer instead of a block barrier per scale: the copies of scale k+1 are issued
     // once every thread has finished gathering from that buffer (scale k-1: a whole per-source phase ago), and the
     // gather of scale k starts once the copies into its buffer have landed -- warps drift by up to one scale.
@@ -229,126 +211,162 @@ __global__ void __launch_bounds__(kBwdThreads, COLVO_MINB_BWD)
       stage_coef(k + 1);
     }
     mbar_wait(&mbar[k & 1], (k >> 1) & 1);                                      // full[k&1]: scale k landed
-    float dD = 0.f;
-    // gather once per scale: every window centre has at most one winning source (texel .w = its index), so its
-    // coefficients go to that source's accumulators (one pass over the 3x3 neighbourhood serves both sources;
-    // exact zeros for the other source -- the three sums cancel heavily against each other downstream)
-    float A[NS][3], Bc[NS][3], G[NS][3];
+    // gather once per scale: every window centre has at most one winning source (its flags weight the lanes), so
+    // one pass over the 3x3 neighbourhood serves all sources with exact zeros for the others (the three sums cancel
+    // heavily against each other downstream)
+    V A[3], Bc[3], G[3];
 #pragma unroll
-    for (int n = 0; n < NS; ++n)
-#pragma unroll
-      for (int ch = 0; ch < 3; ++ch) A[n][ch] = Bc[n][ch] = G[n][ch] = 0.f;
+    for (int ch = 0; ch < 3; ++ch) A[ch] = Bc[ch] = G[ch] = bc<NS>(0.f);
     if (in_img && !COLVO_EXP_NOGATHER) {
 #pragma unroll
       for (int j = 0; j < 9; ++j) {
         const int o = oc + (j / 3) * kCW + (j % 3);
         const float m = my3[j / 3] * mx3[j % 3];
-        float mn[NS];
+        const float4 q3[3] = {cb[o * 3], cb[o * 3 + 1], cb[o * 3 + 2]};
+        V mn;
+        mn.set(0, m * q3[0].w);
+        if (NS > 1) mn.set(NS - 1, m * q3[1].w);
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
-          const float4 q = cb[o * 3 + ch];
-          if (ch == 0) {
-            mn[NS - 1] = m * q.w;                       // q.w is 0 or 1
-            if (NS > 1) mn[0] = m - mn[NS - 1];
-            else mn[0] = m;
-          }
-#pragma unroll
-          for (int n = 0; n < NS; ++n) {
-            A[n][ch] = fmaf(mn[n], q.x, A[n][ch]);
-            Bc[n][ch] = fmaf(mn[n], q.y, Bc[n][ch]);
-            G[n][ch] = fmaf(mn[n], q.z, G[n][ch]);
-          }
+          A[ch] = fma2(mn, bc<NS>(q3[ch].x), A[ch]);
+          Bc[ch] = fma2(mn, bc<NS>(q3[ch].y), Bc[ch]);
+          G[ch] = fma2(mn, bc<NS>(q3[ch].z), G[ch]);
         }
       }
     }
     mbar_arrive(&mbar[2 + (k & 1)]);          // done reading coefficient buffer k & 1
-    const float D_own = gt[0].w;
+    float dD = 0.f;
+    if (in_img) {
+      const BwdConstV<NS> cc = cst[k];
+      // The per-source chain runs on M lanes at a time: M = NS (both sources packed) or M = 1 (one source after the
+      // other: fewer live registers, more issue slots) -- COLVO_BWD_CHAIN_PACKED.
+      constexpr int M = (NS > 1 && COLVO_BWD_CHAIN_PACKED) ? NS : 1;
+      typedef Vn<M> VM;
+      typedef LaneSub<M, NS> LS;
 #pragma unroll
-    for (int n = 0; n < NS; ++n) {
-      if (in_img) {
-        const Img<PK> src = img_at<PK>(P, P.srcs, b * P.src_bf + n * P.src_nf);
-        Pose pose;
+      for (int n0 = 0; n0 < NS; n0 += M) {
+        const VM gu_ = LS::get(gu, n0), gv_ = LS::get(gv, n0), giz_ = LS::get(giz, n0);
+        const VM c_a = LS::get(cc.a, n0), c_b = LS::get(cc.b, n0), c_l0 = LS::get(cc.l0, n0), c_ly = LS::get(cc.ly, n0),
+                 c_lx = LS::get(cc.lx, n0);
+        // taps and texels at the saved coordinates
+        Taps t[M];
+        Texels tx4[M];
+        int r0[M], r1[M];
 #pragma unroll
-        for (int i = 0; i < 9; ++i) pose.r[i] = pose_s[n][i];
+        for (int i = 0; i < M; ++i) {
+          const Img<PK> src = img_at<PK>(P, P.srcs, b * P.src_bf + (n0 + i) * P.src_nf);
+          t[i] = make_taps(gu_.lane(i), gv_.lane(i), P.W, P.H);
+          r0[i] = t[i].y0 * P.W;
+          r1[i] = t[i].y1 * P.W;
+          src.load_taps(r0[i] + t[i].x0, r0[i] + t[i].x1, r1[i] + t[i].x0, r1[i] + t[i].x1, tx4[i]);
+        }
+        VM wx, wy, wl1, vm, gxm, gym;
 #pragma unroll
-        for (int i = 0; i < 3; ++i) pose.t[i] = pose_s[n][9 + i];
-        const BwdConst c = cst[n][k];
-        Geo g;
-        g.u = gt[n].x; g.v = gt[n].y; g.iz = gt[n].z; g.rx = own_rx; g.ry = own_ry;
-        g.valid = (__float_as_uint(gt[n].w) & 1u) != 0u;
-#if COLVO_BWD_PIPE
-        const Taps t = tp[n];
-        const Texels& tx4 = tq[n];
-        const int r0 = t.y0 * P.W, r1 = t.y1 * P.W;
-#else
-        const Taps t = make_taps(g.u, g.v, P.W, P.H);
-        Texels tx4;
-        const int r0 = t.y0 * P.W, r1 = t.y1 * P.W;
-        src.load_taps(r0 + t.x0, r0 + t.x1, r1 + t.x0, r1 + t.x1, tx4);
-#endif
-        const float wl1 = (own_sel == NS + n) ? c.wl1 : 0.f;
-        float du = 0.f, dv = 0.f, hq[3];
+        for (int i = 0; i < M; ++i) {
+          wx.set(i, t[i].wx);
+          wy.set(i, t[i].wy);
+          wl1.set(i, (own_sel == NS + n0 + i) ? cc.wl1.lane(n0 + i) : 0.f);
+          vm.set(i, gvalid[n0 + i] ? 1.f : 0.f);
+          gxm.set(i, t[i].gx ? 1.f : 0.f);       // the coordinate gradient passes strictly inside the border only
+          gym.set(i, t[i].gy ? 1.f : 0.f);
+        }
+        VM du = bc<M>(0.f), dv = bc<M>(0.f), hq[3];
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
+          VM i00, i01, i10, i11;
+#pragma unroll
+          for (int i = 0; i < M; ++i) {
+            i00.set(i, tx4[i].i00[ch]); i01.set(i, tx4[i].i01[ch]); i10.set(i, tx4[i].i10[ch]); i11.set(i, tx4[i].i11[ch]);
+          }
           // bilinear sample and its coordinate derivatives from one cross term
-          const float d01 = tx4.i01[ch] - tx4.i00[ch], e10 = tx4.i10[ch] - tx4.i00[ch];
-          const float cross = (tx4.i11[ch] - tx4.i10[ch]) - d01;
-          const float dux = fmaf(t.wy, cross, d01), dvy = fmaf(t.wx, cross, e10);
-          const float xq = fmaf(t.wy, dvy, fmaf(t.wx, d01, tx4.i00[ch]));
-          const float diff = fmaf(c.a, xq, c.b) - yq[ch];
-          float h = fmaf(xq, Bc[n][ch], fmaf(yq[ch], G[n][ch], A[n][ch]));
-          h = fmaf(wl1, sgn(diff), h);
-          const float lcc = fmaf(c.lx, xq, fmaf(c.ly, yq[ch], c.l0));
-          h += g.valid ? lcc : 0.f;
+          const VM d01 = i01 - i00, e10 = i10 - i00;
+          const VM cross = (i11 - i10) - d01;
+          const VM dux = fma2(wy, cross, d01), dvy = fma2(wx, cross, e10);
+          const VM xq = fma2(wy, dvy, fma2(wx, d01, i00));
+          const VM diff = fma2(c_a, xq, c_b) - bc<M>(yq[ch]);
+          VM h = fma2(xq, LS::get(Bc[ch], n0), fma2(bc<M>(yq[ch]), LS::get(G[ch], n0), LS::get(A[ch], n0)));
+          VM sg;
+#pragma unroll
+          for (int i = 0; i < M; ++i) sg.set(i, sgn_mul(wl1.lane(i), diff.lane(i)));
+          const VM lcc = fma2(c_lx, xq, fma2(c_ly, bc<M>(yq[ch]), c_l0));
+#ifdef COLVO_DEBUG_DUMP
+          if (g_colvo_dbg && k == 0 && n0 == 0 && ch == 0) {
+            float* o = g_colvo_dbg + ((long long)b * P.HW + py * P.W + px) * 12;
+            o[0] = c_a.lane(0); o[1] = c_b.lane(0); o[2] = wl1.lane(0); o[3] = (float)own_sel; o[4] = diff.lane(0);
+            o[5] = sg.lane(0); o[6] = h.lane(0); o[7] = xq.lane(0); o[8] = yq[0]; o[9] = lcc.lane(0); o[10] = vm.lane(0);
+            o[11] = cc.wl1.lane(0);
+          }
+#endif
+          h = fma2(vm, lcc, h + sg);
           hq[ch] = h;
-          du = fmaf(h, dux, du);
-          dv = fmaf(h, dvy, dv);
+          du = fma2(h, dux, du);
+          dv = fma2(h, dvy, dv);
         }
+        const VM w11 = wx * wy, w01 = wx - w11, w10 = wy - w11, w00 = (bc<M>(1.f) - wx) - w10;
         if (gsrc4 && !COLVO_EXP_NORED) {
           // scatter into the texel-interleaved gradient buffer: one 16-byte vector RED per tap carries the three
           // channels (a third of the L2 atomic requests of a planar scatter); null for packed sources, whose
           // quantised images carry no gradient
-          const float w11 = t.wx * t.wy, w01 = t.wx - w11, w10 = t.wy - w11, w00 = 1.f - t.wx - w10;
-          float4* gs = gsrc4 + (long long)(b * P.N + n) * P.HW;
-          asm volatile("" : "+l"(gs));      // materialised base: one IMAD.WIDE per address (see Img<false>::load_taps)
-          red_add3(gs + (unsigned)(r0 + t.x0), w00 * hq[0], w00 * hq[1], w00 * hq[2]);
-          red_add3(gs + (unsigned)(r0 + t.x1), w01 * hq[0], w01 * hq[1], w01 * hq[2]);
-          red_add3(gs + (unsigned)(r1 + t.x0), w10 * hq[0], w10 * hq[1], w10 * hq[2]);
-          red_add3(gs + (unsigned)(r1 + t.x1), w11 * hq[0], w11 * hq[1], w11 * hq[2]);
+#pragma unroll
+          for (int i = 0; i < M; ++i) {
+            float4* gs = gsrc4 + (long long)(b * P.N + n0 + i) * P.HW;
+            asm volatile("" : "+l"(gs));      // materialised base: one IMAD.WIDE per address (see Img<false>::load_taps)
+            const float a00 = w00.lane(i), a01 = w01.lane(i), a10 = w10.lane(i), a11 = w11.lane(i);
+            const float h0 = hq[0].lane(i), h1 = hq[1].lane(i), h2 = hq[2].lane(i);
+            red_add3(gs + (unsigned)(r0[i] + t[i].x0), a00 * h0, a00 * h1, a00 * h2);
+            red_add3(gs + (unsigned)(r0[i] + t[i].x1), a01 * h0, a01 * h1, a01 * h2);
+            red_add3(gs + (unsigned)(r1[i] + t[i].x0), a10 * h0, a10 * h1, a10 * h2);
+            red_add3(gs + (unsigned)(r1[i] + t[i].x1), a11 * h0, a11 * h1, a11 * h2);
+          }
         }
         // geometric consistency (f-2): gradient to Z' directly, to the sampled source depth (scatter) and,
         // through its spatial derivative, to (u', v')
-        float dZp_direct = 0.f;
-        if (GEO && g.valid) {
-          float d4[4], dZ, dS;
-          const float ds = sample_plane(P.src_depth + (long long)(b * P.N + n) * P.HW, t, P.W, d4);
-          geo_diff(p_sub(p_rcp(g.iz), P.eps_proj), ds, dZ, dS);     // Z' back from iz = 1 / (Z' + eps)
-          const float wg = go * P.geo_weight / ((float)P.S * (float)P.B * (float)P.N * (float)P.HW);
-          dZp_direct = wg * dZ;
-          const float gS = wg * dS;
-          du += gS * ((1.f - t.wy) * (d4[1] - d4[0]) + t.wy * (d4[3] - d4[2]));
-          dv += gS * ((1.f - t.wx) * (d4[2] - d4[0]) + t.wx * (d4[3] - d4[1]));
-          if (grad_src_depth) {
-            const float w11 = t.wx * t.wy, w01 = t.wx - w11, w10 = t.wy - w11, w00 = 1.f - t.wx - w10;
-            float* gd = grad_src_depth + (long long)(b * P.N + n) * P.HW;
-            atomicAdd(gd + (r0 + t.x0), w00 * gS);
-            atomicAdd(gd + (r0 + t.x1), w01 * gS);
-            atomicAdd(gd + (r1 + t.x0), w10 * gS);
-            atomicAdd(gd + (r1 + t.x1), w11 * gS);
+        VM dZp_direct = bc<M>(0.f);
+        if (GEO) {
+#pragma unroll
+          for (int i = 0; i < M; ++i) {
+            if (gvalid[n0 + i]) {
+              float d4[4], dZ, dS;
+              const float ds = sample_plane(P.src_depth + (long long)(b * P.N + n0 + i) * P.HW, t[i], P.W, d4);
+              geo_diff(p_sub(p_rcp(giz_.lane(i)), P.eps_proj), ds, dZ, dS);     // Z' back from iz = 1 / (Z' + eps)
+              const float wg = go * P.geo_weight / ((float)P.S * (float)P.B * (float)P.N * (float)P.HW);
+              dZp_direct.set(i, wg * dZ);
+              const float gS = wg * dS;
+              du.set(i, du.lane(i) + gS * ((1.f - t[i].wy) * (d4[1] - d4[0]) + t[i].wy * (d4[3] - d4[2])));
+              dv.set(i, dv.lane(i) + gS * ((1.f - t[i].wx) * (d4[2] - d4[0]) + t[i].wx * (d4[3] - d4[1])));
+              if (grad_src_depth) {
+                float* gd = grad_src_depth + (long long)(b * P.N + n0 + i) * P.HW;
+                atomicAdd(gd + (r0[i] + t[i].x0), w00.lane(i) * gS);
+                atomicAdd(gd + (r0[i] + t[i].x1), w01.lane(i) * gS);
+                atomicAdd(gd + (r1[i] + t[i].x0), w10.lane(i) * gS);
+                atomicAdd(gd + (r1[i] + t[i].x1), w11.lane(i) * gS);
+              }
+            }
           }
         }
-        if (!t.gx) du = 0.f;
-        if (!t.gy) dv = 0.f;
-        float dXp[3];
-        dD += project_adjoint(g, cam, pose, du, dv, dZp_direct, dXp);
+        du = du * gxm;
+        dv = dv * gym;
+        // projection / transform / back-projection adjoint (colvo_math.cuh::project_adjoint)
+        const VM dx = du * giz_, dy = dv * giz_;
+        VM dXp[3];
+        dXp[0] = bc<M>(cam.fx) * dx;
+        dXp[1] = bc<M>(cam.fy) * dy;
+        dXp[2] = fma2(bc<M>(cam.cx), dx, fma2(bc<M>(cam.cy), dy, fma2(-giz_, fma2(du, gu_, dv * gv_), dZp_direct)));
+        VM R[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) R[i] = LS::get(pose_s[i], n0);
+        const VM dX = fma2(R[0], dXp[0], fma2(R[3], dXp[1], R[6] * dXp[2]));
+        const VM dY = fma2(R[1], dXp[0], fma2(R[4], dXp[1], R[7] * dXp[2]));
+        const VM dZ = fma2(R[2], dXp[0], fma2(R[5], dXp[1], R[8] * dXp[2]));
+        const VM dDv = fma2(bc<M>(own_rx), dX, fma2(bc<M>(own_ry), dY, dZ));
+#pragma unroll
+        for (int i = 0; i < M; ++i) dD += dDv.lane(i);
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-          pw[n][i] = fmaf(dXp[i], D_own, pw[n][i]);
-          pt[n][i] += dXp[i];
+          LS::put(pw[i], n0, fma2(dXp[i], bc<M>(D_own), LS::get(pw[i], n0)));
+          LS::put(pt[i], n0, LS::get(pt[i], n0) + dXp[i]);
         }
       }
-    }
-    if (in_img) {
       const int p = py * P.W + px;
       if (k == 0) {
         const float s = __ldg(s_field0 + (long long)b * P.HW + p);
@@ -367,7 +385,8 @@ __global__ void __launch_bounds__(kBwdThreads, COLVO_MINB_BWD)
 #pragma unroll
   for (int n = 0; n < NS; ++n) {
     float gp[12];
-    pose_grad_expand(pw[n], pt[n], own_rx, own_ry, gp);
+    const float w[3] = {pw[0].lane(n), pw[1].lane(n), pw[2].lane(n)}, tt[3] = {pt[0].lane(n), pt[1].lane(n), pt[2].lane(n)};
+    pose_grad_expand(w, tt, own_rx, own_ry, gp);
 #pragma unroll
     for (int j = 0; j < 12; ++j) slots[(n * 12 + j) * kBwdThreads + tid] = in_img ? gp[j] : 0.f;
   }

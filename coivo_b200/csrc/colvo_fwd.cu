@@ -8,6 +8,8 @@
 //   k_photo_fwd     (colvo_photo_fwd.cuh) per 32x12 tile, strip walk: identity + re-projection candidates,
 //                   SSIM+L1, min-reprojection / auto-mask, loss partials, dL/da, dL/db  (rows 6-8)
 //   k_finalize_fwd  deterministic final sums -> loss, G_a, G_b, sum s*d               (row 10)
+#include <type_traits>
+
 #include "colvo_kernels.cuh"
 #include "colvo_photo_fwd.cuh"
 
@@ -187,16 +189,22 @@ __global__ void __launch_bounds__(kThreads)
 }
 
 // ------------------------------------------------------------------------------------------
-// One CTA = one (b, k) and a chunk of pixels; both sources are warped by the same thread so the
-// ray, the up-sampled depth and the target pixel are loaded once.  The raw warped frames are also
-// written out ([B,N,S,3,H,W] scratch): the tile kernel needs them with a halo, and re-warping there
-// costs more issue slots than the 12 B/pixel round trip costs bandwidth on this ALU-bound path.
+// One CTA = one (b, k) and a chunk of pixels; all sources are warped by the same thread so the ray, the
+// up-sampled depth and the target pixel are loaded once, and with N = 2 the two sources ride in the two lanes
+// of packed fp32x2 registers (reprojection chain, bilinear blend, LCC products: FMUL2 / FADD2 / FFMA2 --
+// the pinned chain stays single-rounded per lane, so `valid` is bit-exact as before).
+// The raw warped frames are written out for the tile kernel, which needs them with a halo (re-warping there
+// costs more issue slots than the round trip costs bandwidth on this ALU-bound path):
+//   N = 1:  iw[(b,k)][pix] = (x0, x1, x2, valid)                                   16 B / pixel
+//   N = 2:  iwA[(b,k)][pix] = (x0^0, x0^1, x1^0, x1^1), iwB[(b,k)][pix] = (x2^0, x2^1)   24 B / pixel for both sources
+// (iwB starts B*S*HW float4 behind iw), i.e. channel c of both sources is one aligned register pair downstream.
 template <int NS, bool GEO, bool PK>
 __global__ void __launch_bounds__(kThreads, COLVO_MINB_STATS)
     k_warp_stats(KP P, double* __restrict__ part, uint8_t* __restrict__ valid_out, float4* __restrict__ iw_out,
                  float4* __restrict__ geo_out) {
   constexpr int NA = GEO ? kStatVals : 5;      // accumulators per source (the 6th only with the geometric term)
   constexpr int NV = NA * NS;
+  typedef Vn<NS> V;
   __shared__ double sm[(kThreads / 32) * NV];
   pdl_trigger();                               // k_lcc_solve / k_photo_fwd may start their prologues in this kernel's tail
   const int bk = blockIdx.y, k = bk % P.S, b = bk / P.S;
@@ -211,12 +219,15 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_STATS)
   const unsigned out_nstride = (unsigned)P.S * (unsigned)P.HW, hw = P.HW;
   const long long out_bk = (long long)(b * P.N * P.S + k) * P.HW;
   uint8_t* valid_b = valid_out ? valid_out + out_bk : nullptr;
-  float4* iw_b = iw_out ? iw_out + out_bk : nullptr;
-  float4* geo_b = geo_out ? geo_out + out_bk : nullptr;
-  asm volatile("" : "+l"(tg.p), "+l"(src0.p), "+l"(valid_b), "+l"(iw_b), "+l"(geo_b));
-  Pose pose[NS];
-#pragma unroll
-  for (int n = 0; n < NS; ++n) pose[n] = load_pose(P, b, n);
+  // saved projection: N = 1 one texel array; N = 2 the planes A = (u^0, u^1, v^0, v^1) and B = (iz^0, iz^1, D^, valid bits)
+  float4* geo_b = geo_out ? geo_out + (long long)(b * P.S + k) * P.HW : nullptr;
+  float4* geo_b2 = (geo_out && NS == 2) ? geo_out + (long long)((P.B + b) * P.S + k) * P.HW : nullptr;
+  // warped frames: N = 1 one texel array; N = 2 the pair planes A (float4) and B (float2) indexed by (b, k)
+  float4* iw_a = iw_out ? iw_out + (NS == 1 ? out_bk : (long long)(b * P.S + k) * P.HW) : nullptr;
+  float2* iw_b2 = (iw_out && NS == 2) ? reinterpret_cast<float2*>(iw_out + (long long)P.B * P.S * P.HW) + (long long)(b * P.S + k) * P.HW
+                                      : nullptr;
+  asm volatile("" : "+l"(tg.p), "+l"(src0.p), "+l"(valid_b), "+l"(iw_a), "+l"(iw_b2), "+l"(geo_b), "+l"(geo_b2));
+  const PoseV<NS> pose = load_pose_v<NS>(P, b);
   int pix = blockIdx.x * (kThreads * kStatPPT) + threadIdx.x;
   int py = pix / P.W, px = pix - py * P.W;
   double acc[NV];
@@ -237,27 +248,70 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_STATS)
         const unsigned upix = pix;
         y0 = __ldg(tg.p + upix); y1 = __ldg(tg.p + (upix + hw)); y2 = __ldg(tg.p + (upix + 2 * hw));
       }
+      const GeoV<NS> g = reproject_v<NS>(rx, ry, D, cam, pose, P.W, P.H, P.eps_proj, P.z_min);
+      Taps t[NS];
+      Texels tx[NS];
 #pragma unroll
       for (int n = 0; n < NS; ++n) {
-        Geo g; Taps t; Texels tx; float x[3];
-        warp_sample<PK>(P, src0, cam, pose[n], rx, ry, D, g, t, tx, x, n * src_noff);
+        t[n] = make_taps(g.u.lane(n), g.v.lane(n), P.W, P.H);
+        const int foff = n * src_noff;
+        const int r0 = foff + t[n].y0 * P.W, r1 = foff + t[n].y1 * P.W;
+        src0.load_taps(r0 + t[n].x0, r0 + t[n].x1, r1 + t[n].x0, r1 + t[n].x1, tx[n]);
+      }
+      // bilinear blend of all sources, lane by lane the arithmetic of colvo_math.cuh::bilerp
+      V wx, wy, x[3];
+#pragma unroll
+      for (int n = 0; n < NS; ++n) { wx.set(n, t[n].wx); wy.set(n, t[n].wy); }
+      const V omx = bc<NS>(1.0f) - wx, omy = bc<NS>(1.0f) - wy;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        V i00, i01, i10, i11;
+#pragma unroll
+        for (int n = 0; n < NS; ++n) {
+          i00.set(n, tx[n].i00[c]); i01.set(n, tx[n].i01[c]); i10.set(n, tx[n].i10[c]); i11.set(n, tx[n].i11[c]);
+        }
+        const V top = fma2(wx, i01, omx * i00), bot = fma2(wx, i11, omx * i10);
+        x[c] = fma2(wy, bot, omy * top);
+      }
+      // raw warped frames, re-used by k_photo_fwd instead of warping again (+halo)
+      if (iw_a) {
+        if constexpr (NS == 1) {
+          iw_a[pix] = make_float4(x[0].lane(0), x[1].lane(0), x[2].lane(0), g.valid[0] ? 1.f : 0.f);
+        } else {
+          iw_a[pix] = make_float4(x[0].lane(0), x[0].lane(1), x[1].lane(0), x[1].lane(1));
+          iw_b2[pix] = make_float2(x[2].lane(0), x[2].lane(1));
+        }
+      }
+      // the projection itself, for the backward
+      if (geo_b) {
+        if constexpr (NS == 1) {              // valid rides in the mantissa LSB of the depth
+          geo_b[pix] = make_float4(g.u.lane(0), g.v.lane(0), g.iz.lane(0),
+                                   __uint_as_float((__float_as_uint(D) & ~1u) | (g.valid[0] ? 1u : 0u)));
+        } else {
+          geo_b[pix] = make_float4(g.u.lane(0), g.u.lane(1), g.v.lane(0), g.v.lane(1));
+          geo_b2[pix] = make_float4(g.iz.lane(0), g.iz.lane(1), D,
+                                    __uint_as_float((g.valid[0] ? 1u : 0u) | (g.valid[NS - 1] ? 2u : 0u)));
+        }
+      }
+      // LCC products of all sources
+      const V s1 = x[0] + x[1] + x[2];
+      const V s2 = fma2(x[2], x[2], fma2(x[1], x[1], x[0] * x[0]));
+      const V s3 = fma2(x[2], bc<NS>(y2), fma2(x[1], bc<NS>(y1), x[0] * bc<NS>(y0)));
+      const float sy = y0 + y1 + y2;
+#pragma unroll
+      for (int n = 0; n < NS; ++n) {
         const unsigned opix = (unsigned)pix + n * out_nstride;
-        if (valid_b) valid_b[opix] = g.valid ? 1 : 0;
-        // raw warped frame, re-used by k_photo_fwd instead of warping again (+halo): one 16-byte texel
-        if (iw_b) iw_b[opix] = make_float4(x[0], x[1], x[2], g.valid ? 1.f : 0.f);
-        // the projection itself, for the backward (valid rides in the mantissa LSB of the depth)
-        if (geo_b)
-          geo_b[opix] = make_float4(g.u, g.v, g.iz, __uint_as_float((__float_as_uint(D) & ~1u) | (g.valid ? 1u : 0u)));
-        if (g.valid) {
+        if (valid_b) valid_b[opix] = g.valid[n] ? 1 : 0;
+        if (g.valid[n]) {
           acc[NA * n + 0] += 3.0;
-          acc[NA * n + 1] += (double)(x[0] + x[1] + x[2]);
-          acc[NA * n + 2] += (double)(y0 + y1 + y2);
-          acc[NA * n + 3] += (double)(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
-          acc[NA * n + 4] += (double)(x[0] * y0 + x[1] * y1 + x[2] * y2);
+          acc[NA * n + 1] += (double)s1.lane(n);
+          acc[NA * n + 2] += (double)sy;
+          acc[NA * n + 3] += (double)s2.lane(n);
+          acc[NA * n + 4] += (double)s3.lane(n);
           if (GEO) {               // geometric consistency (f-2): per-pixel, so it lives in this pass
             float d4[4], dZ, dS;
-            const float ds = sample_plane(P.src_depth + (long long)(b * P.N + n) * P.HW, t, P.W, d4);
-            acc[NA * n + (NA - 1)] += (double)geo_diff(g.Zp, ds, dZ, dS);
+            const float ds = sample_plane(P.src_depth + (long long)(b * P.N + n) * P.HW, t[n], P.W, d4);
+            acc[NA * n + (NA - 1)] += (double)geo_diff(g.Zp.lane(n), ds, dZ, dS);
           }
         }
       }
@@ -447,6 +501,7 @@ __global__ void __launch_bounds__(kThreads)
 struct ConsSmem {
   float4 y[kDN];
   float4 x[kDN];
+  float2 xb[1];
   double red[kFwdWarps * 2];
 };
 __global__ void __launch_bounds__(kFwdThreads)
@@ -476,7 +531,8 @@ __global__ void __launch_bounds__(kFwdThreads)
     cp_async_wait_all();
     __syncthreads();
   }
-  const CalK cal = make_calk(__ldg(ab + 2 * b), __ldg(ab + 2 * b + 1));
+  const float cal_a[1] = {__ldg(ab + 2 * b)}, cal_b[1] = {__ldg(ab + 2 * b + 1)};
+  const CalV<1> cal = make_calv<1>(cal_a, cal_b, P.alpha);
   const int trow0 = wid * kFwdRows;
   double acc[2] = {0.0, 0.0};
   RowH<1> R[3];
@@ -484,14 +540,14 @@ __global__ void __launch_bounds__(kFwdThreads)
 #pragma unroll
   for (int j = 0; j < kFwdRows + 2; ++j) {
     const int o = (trow0 + j) * kDW + lane;
-    row_sums<1, true>(R[j % 3], Y[j % 3], sm.y + o, sm.x + o, sm.x + o);
+    row_sums<1, true>(R[j % 3], Y[j % 3], sm.y, sm.x, sm.xb, o);
     if (j >= 2) {
       const int py = y0 + trow0 + j - 2;
       // validity of the window's own pixel: the centre texel of the middle row
       const bool valid = sm.x[(trow0 + j - 1) * kDW + lane + 1].w != 0.f;
       if (py < P.H && px < P.W && valid) {
         WinY wy;
-        float Sx[3], Sxx[3], Sxy[3];
+        Vn<1> Sx[3], Sxx[3], Sxy[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           const float sy = Y[0].sy[c] + Y[1].sy[c] + Y[2].sy[c];
@@ -499,12 +555,10 @@ __global__ void __launch_bounds__(kFwdThreads)
           wy.muy[c] = sy * (1.0f / 9.0f);
           wy.sgy[c] = fmaf(-wy.muy[c], wy.muy[c], syy * (1.0f / 9.0f));
           wy.yc[c] = Y[(j - 1) % 3].yc[c];
-          Sx[c] = R[0].sx[0][c] + R[1].sx[0][c] + R[2].sx[0][c];
-          Sxx[c] = R[0].sxx[0][c] + R[1].sxx[0][c] + R[2].sxx[0][c];
-          Sxy[c] = R[0].sxy[0][c] + R[1].sxy[0][c] + R[2].sxy[0][c];
         }
+        window_sums<1>(R, Sx, Sxx, Sxy);
         winy_derive(wy, P.c1, P.c2);
-        acc[0] += (double)(pe_value3(Sx, Sxx, Sxy, R[(j - 1) % 3].xc[0], wy, cal, P.alpha, P.c1, P.c2) * (1.0f / 3.0f));
+        acc[0] += (double)(pe_value3v<1>(Sx, Sxx, Sxy, R[(j - 1) % 3].xc, wy, cal, P.alpha, P.c1, P.c2).v * (1.0f / 3.0f));
         acc[1] += 1.0;
       }
     }
@@ -573,7 +627,6 @@ cudaError_t launch_forward(const KP& P, const FwdBuffers& Wk, float* loss, float
   cudaError_t e = launch_pdl(k_lcc_solve, dim3(BNS), dim3(32), 0, st, P, Wk.stat_part, Wk.stat_chunks, ab,
                              save ? sv.frame : nullptr);
   if (e != cudaSuccess) return e;
-  if (e != cudaSuccess) return e;
   // The smoothness pass depends on the inputs only; it is launched in two halves of the batch, one behind the
   // statistics pass and one behind the tile kernel, so that each fills the tail of a big launch.
   SmoothOut smo;
@@ -601,8 +654,15 @@ cudaError_t launch_forward(const KP& P, const FwdBuffers& Wk, float* loss, float
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       e = launch_pdl(kern, grid, dim3(kFwdThreads), smem, st, P, ab, sel, Wk.loss_part, Wk.g_part, need_g, co, Wk.iw);
     };
-    if (P.N == 1) { if (pk) run(k_photo_fwd<1, true>, photo_fwd_smem<1>()); else run(k_photo_fwd<1, false>, photo_fwd_smem<1>()); }
-    else { if (pk) run(k_photo_fwd<2, true>, photo_fwd_smem<2>()); else run(k_photo_fwd<2, false>, photo_fwd_smem<2>()); }
+    auto pick = [&](auto ns, auto pkc) {          // ADJ: the adjoint pieces are needed only when the forward saves for a backward
+      constexpr int NSc = decltype(ns)::value;
+      constexpr bool PKc = decltype(pkc)::value;
+      if (save) run(k_photo_fwd<NSc, PKc, true>, photo_fwd_smem<NSc>());
+      else run(k_photo_fwd<NSc, PKc, false>, photo_fwd_smem<NSc>());
+    };
+    using I1 = std::integral_constant<int, 1>; using I2 = std::integral_constant<int, 2>;
+    if (P.N == 1) { if (pk) pick(I1{}, std::true_type{}); else pick(I1{}, std::false_type{}); }
+    else { if (pk) pick(I2{}, std::true_type{}); else pick(I2{}, std::false_type{}); }
   }
   if (e != cudaSuccess) return e;
   run_smooth(b_first, P.B - b_first);

@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include "colvo_math.cuh"
+#include "colvo_f2.cuh"
 
 namespace colvo {
 
@@ -96,6 +97,48 @@ __device__ __forceinline__ Pose load_pose(const KP& P, int b, int n) {
     p.t[i] = __ldg(t + 4 * i + 3);
   }
   return p;
+}
+
+// The N source poses of a triplet, lane n = source n (one register pair per entry for N = 2)
+template <int NS>
+struct PoseV { Vn<NS> r[9], t[3]; };
+template <int NS>
+__device__ __forceinline__ PoseV<NS> load_pose_v(const KP& P, int b) {
+  PoseV<NS> p;
+#pragma unroll
+  for (int n = 0; n < NS; ++n) {
+    const Pose q = load_pose(P, b, n);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) p.r[i].set(n, q.r[i]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) p.t[i].set(n, q.t[i]);
+  }
+  return p;
+}
+// rows 1-3 for all sources at once: the same pinned chain as colvo_math.cuh::reproject_ray, lane by lane
+template <int NS>
+struct GeoV { Vn<NS> u, v, iz, Zp; bool valid[NS]; };
+template <int NS>
+__device__ __forceinline__ GeoV<NS> reproject_v(float rx, float ry, float D, const Cam& c, const PoseV<NS>& p, int W, int H,
+                                                float eps, float z_min) {
+  typedef Vn<NS> V;
+  const V X = V(p_mul(rx, D)), Y = V(p_mul(ry, D)), Z = V(D);
+  const V Xp = padd(padd(padd(pmul(p.r[0], X), pmul(p.r[1], Y)), pmul(p.r[2], Z)), p.t[0]);
+  const V Yp = padd(padd(padd(pmul(p.r[3], X), pmul(p.r[4], Y)), pmul(p.r[5], Z)), p.t[1]);
+  const V Zp = padd(padd(padd(pmul(p.r[6], X), pmul(p.r[7], Y)), pmul(p.r[8], Z)), p.t[2]);
+  const V x = padd(pmul(V(c.fx), Xp), pmul(V(c.cx), Zp));
+  const V y = padd(pmul(V(c.fy), Yp), pmul(V(c.cy), Zp));
+  GeoV<NS> g;
+  g.Zp = Zp;
+  g.iz = prcp(padd(Zp, V(eps)));
+  g.u = pmul(x, g.iz);
+  g.v = pmul(y, g.iz);
+#pragma unroll
+  for (int n = 0; n < NS; ++n) {
+    const float u = g.u.lane(n), v = g.v.lane(n);
+    g.valid[n] = (u >= 0.f) && (u <= (float)(W - 1)) && (v >= 0.f) && (v <= (float)(H - 1)) && (Zp.lane(n) > z_min);
+  }
+  return g;
 }
 
 // Row 0: up-sampled depth at a full-resolution pixel (identity at k == 0).
@@ -220,6 +263,9 @@ __device__ __forceinline__ float4 ldg_f4_hint(const float4* p, unsigned long lon
 // the same with the 32-bit shared-window address already at hand (hoisted out of an unrolled staging loop)
 __device__ __forceinline__ void cp_async16_s(unsigned saddr, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async8_s(unsigned saddr, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(saddr), "l"(gmem));
 }
 __device__ __forceinline__ void cp_async4_s(unsigned saddr, const void* gmem) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(saddr), "l"(gmem));

@@ -170,7 +170,16 @@ CV_HD SsimParts ssim_parts(float mut, float st, float stxy, float muy, float sy,
 CV_HD float clamp01(float t) { return fminf(fmaxf(t, 0.f), 1.f); }
 CV_HD float sgn(float x) { return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f); }
 // w * sgn(x) with sgn(0) = 0 (torch's sub-gradient of |.|): copysign + one select instead of two compares and a convert
-CV_HD float sgn_scaled(float w, float x) { return (x != 0.f) ? copysignf(w, x) * 1.0f : 0.f; }
+CV_HD float sgn_scaled(float w, float x) { return (x != 0.f) ? copysignf(w, x) : 0.f; }     // w >= 0 only
+// w * sgn(x) for a weight of either sign (the LCC gain, hence the L1 weight of the backward, can be negative):
+// the sign bit of x is xor-ed onto w
+CV_HD float sgn_mul(float w, float x) {
+#if defined(__CUDA_ARCH__)
+  return (x != 0.f) ? __uint_as_float(__float_as_uint(w) ^ (__float_as_uint(x) & 0x80000000u)) : 0.f;
+#else
+  return (x > 0.f) ? w : ((x < 0.f) ? -w : 0.f);
+#endif
+}
 
 // coefficient fields of the SSIM adjoint in gather form (re-derived for
 // raw moments):  d pe_p / d x_q  =  ca_p + x_q * cb_p + y_q * cg_p   for every occurrence of q in

@@ -40,14 +40,26 @@ def global_mean_loss(local_loss: torch.Tensor, local_count: int, group=None) -> 
     return (buf[0] / buf[1]).to(local_loss.dtype)
 
 
-def sharded_loss(loss_fn: Callable[..., torch.Tensor], batch: Dict[str, object], *, group=None, **kw):
+def sharded_loss(loss_fn: Callable[..., torch.Tensor], batch: Dict[str, object], *, group=None, reduce: str = "sum", **kw):
     """Run `loss_fn(depth, pose, K, tgt, srcs)` on this rank's shard and return
-    (local loss scaled so that summing gradients over ranks gives the global-mean gradient,
-    global mean loss).  `loss_fn` is `coivo_b200.photometric_loss` in production."""
+    `(local loss to back-propagate, global mean loss)`.  `loss_fn` is `coivo_b200.photometric_loss` in production.
+
+    The scale of the returned local loss depends on how the caller combines gradients across ranks:
+
+    * `reduce="sum"` (default): `local * (B_g / B)`.  SUMMING the per-rank gradients (all-reduce with
+      `ReduceOp.SUM`, or simply keeping per-sample gradients local) gives the gradient of the global mean.
+    * `reduce="mean"`: `local * (B_g * world / B)`.  AVERAGING the per-rank gradients gives the gradient of the
+      global mean -- this is what `torch.nn.parallel.DistributedDataParallel` does (it divides the summed
+      gradients by `world_size`), so use it when the depth / pose networks are wrapped in DDP.  For balanced
+      shards the factor is exactly 1.
+    """
+    if reduce not in ("sum", "mean"):
+        raise ValueError("reduce must be 'sum' or 'mean'")
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     B = batch["tgt"].shape[0]
     sh = shard_batch(batch, rank, world)
     nloc = sh["tgt"].shape[0]
     local = loss_fn(sh["depth"], sh["pose"], sh["K"], sh["tgt"], sh["srcs"], **kw)
     glob = global_mean_loss(local, nloc, group)
-    return local * (nloc / B), glob
+    scale = nloc / B if reduce == "sum" else nloc * world / B
+    return local * scale, glob

@@ -42,6 +42,7 @@ class _PoseFn(torch.autograd.Function):
         return T
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, gT):
         axisangle, translation = ctx.saved_tensors
         lib = _lib.load()
@@ -84,6 +85,7 @@ class _DispFn(torch.autograd.Function):
         return tuple(depth)
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, *gdepth):
         depth = ctx.saved_tensors
         lib = _lib.load()

@@ -35,16 +35,20 @@ class GraphedStep:
         torch.cuda.synchronize(dev)
         for t in self._leaves:
             t.grad = None
-        # the leaves' AccumulateGrad nodes were created on the warm-up stream; capture runs on its own stream
-        try:
-            torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
-        except AttributeError:
-            pass
         self._one = torch.ones((), dtype=torch.float32, device=dev)     # d loss / d loss, made once (no fill in the graph)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.loss = photometric_loss(self.depth, self.pose, self.K, self.tgt, self.srcs, **self.kw)
-            self.loss.backward(gradient=self._one)
+        # the leaves' AccumulateGrad nodes were created on the warm-up stream and capture runs on its own stream: the
+        # stream-mismatch warning is silenced for the capture only and put back afterwards
+        setter = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+        if setter is not None:
+            setter(False)
+        try:
+            with torch.cuda.graph(self.graph):
+                self.loss = photometric_loss(self.depth, self.pose, self.K, self.tgt, self.srcs, **self.kw)
+                self.loss.backward(gradient=self._one)
+        finally:
+            if setter is not None:
+                setter(True)
 
     def _eager(self):
         for t in self._leaves:

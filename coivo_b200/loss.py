@@ -12,7 +12,9 @@ memory, the current stream and autograd plumbing.  CUDA-only: CPU tensors are re
 """
 from __future__ import annotations
 
+import collections
 import ctypes
+import functools
 from typing import List, Optional, Sequence
 
 import torch
@@ -87,9 +89,11 @@ def _check_inputs(depth, pose, K, tgt, srcs):
 
 
 class _Workspace:
-    """One scratch buffer per (device, stream), grown on demand; never shared across streams."""
+    """One scratch buffer per (device, stream), grown on demand; never shared across streams.  At most `MAX_STREAMS`
+    buffers are kept (least recently used first out), `clear()` drops them all."""
 
-    _bufs = {}
+    MAX_STREAMS = 4
+    _bufs = collections.OrderedDict()
 
     @classmethod
     def get(cls, nbytes: int, device: torch.device) -> torch.Tensor:
@@ -98,7 +102,25 @@ class _Workspace:
         if buf is None or buf.numel() < nbytes:
             buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
             cls._bufs[key] = buf
+        cls._bufs.move_to_end(key)
+        while len(cls._bufs) > cls.MAX_STREAMS:
+            cls._bufs.popitem(last=False)
         return buf
+
+    @classmethod
+    def clear(cls) -> None:
+        cls._bufs.clear()
+
+
+@functools.lru_cache(maxsize=64)
+def _plan(B, N, S, H, W, flags, alpha, smooth_weight, geo_weight):
+    """Descriptor and buffer sizes of one problem shape (cached: two ctypes round trips per shape, not per call)."""
+    lib = _lib.load()
+    desc = _lib.make_desc(B, N, S, H, W, flags, alpha, smooth_weight, geo_weight)
+    nbytes, nsaved = ctypes.c_size_t(), ctypes.c_size_t()
+    _lib.check(lib.colvo_workspace_bytes(ctypes.byref(desc), ctypes.byref(nbytes)), "colvo_workspace_bytes")
+    _lib.check(lib.colvo_saved_doubles(ctypes.byref(desc), ctypes.byref(nsaved)), "colvo_saved_doubles")
+    return desc, nbytes.value, nsaved.value
 
 
 class _PhotoLossFn(torch.autograd.Function):
@@ -114,30 +136,31 @@ class _PhotoLossFn(torch.autograd.Function):
                 raise ValueError("src_depth must be a contiguous tensor on the inputs' device")
         else:
             geo_weight = 0.0
+        if geo_weight == 0.0:
+            src_depth = None          # the term is off: the source depth maps take no part (and get no gradient)
+        if K.requires_grad or tgt.requires_grad:
+            raise ValueError("photometric_loss gives no gradient to K or tgt (oracle A14): detach them")
         lib = _lib.load()
         dev = tgt.device
         needs_grad = any(ctx.needs_input_grad[i] for i in (0, 3, 9)) or any(ctx.needs_input_grad[11:])
         flags = (_lib.F_LCC if lcc else 0) | (_lib.F_LCC_DETACH if lcc_detach else 0) | (_lib.F_PACKED_BF16 if packed else 0)
         if needs_grad:
             flags |= _lib.F_SAVE_FOR_BWD
-        desc = _lib.make_desc(B, N, S, H, W, flags, alpha, smooth_weight, geo_weight)
-        nbytes = ctypes.c_size_t()
-        _lib.check(lib.colvo_workspace_bytes(ctypes.byref(desc), ctypes.byref(nbytes)), "colvo_workspace_bytes")
-        nsaved = ctypes.c_size_t()
-        _lib.check(lib.colvo_saved_doubles(ctypes.byref(desc), ctypes.byref(nsaved)), "colvo_saved_doubles")
+        desc, nbytes, nsaved = _plan(B, N, S, H, W, flags, alpha, smooth_weight, geo_weight)
         with torch.cuda.device(dev):
-            ws = _Workspace.get(nbytes.value, dev)
+            ws = _Workspace.get(nbytes, dev)
             loss = torch.empty((), dtype=torch.float32, device=dev)
             ab = torch.empty(B, N, S, 2, dtype=torch.float32, device=dev)
             sel = torch.empty(B, S, H, W, dtype=torch.uint8, device=dev)
-            saved = torch.empty(nsaved.value, dtype=torch.float64, device=dev)
+            # forward -> backward state: only when a backward can follow (validation / no_grad allocates nothing)
+            saved = torch.empty(nsaved, dtype=torch.float64, device=dev) if needs_grad else None
             valid = torch.empty(B, N, S, H, W, dtype=torch.uint8, device=dev) if want_valid else None
             stream = torch.cuda.current_stream(dev).cuda_stream
             rc = lib.colvo_photo_forward(
                 ctypes.byref(desc), tgt.data_ptr(), srcs.data_ptr(), _lib.ptr_array([d.data_ptr() for d in depth]),
                 K.data_ptr(), pose.data_ptr(), src_depth.data_ptr() if src_depth is not None else None, loss.data_ptr(),
-                ab.data_ptr(), valid.data_ptr() if valid is not None else None, sel.data_ptr(), saved.data_ptr(),
-                ws.data_ptr(), ws.numel(), stream)
+                ab.data_ptr(), valid.data_ptr() if valid is not None else None, sel.data_ptr(),
+                saved.data_ptr() if saved is not None else None, ws.data_ptr(), ws.numel(), stream)
         _lib.check(rc, "colvo_photo_forward")
         ctx.desc_args = (B, N, S, H, W, flags, alpha, smooth_weight, geo_weight)
         ctx.n_depth = S
@@ -153,6 +176,7 @@ class _PhotoLossFn(torch.autograd.Function):
         return loss, ab, sel
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, grad_loss, *unused):
         if grad_loss is None:                 # the loss itself was not used
             return (None,) * (11 + ctx.n_depth)
@@ -165,11 +189,9 @@ class _PhotoLossFn(torch.autograd.Function):
             flags |= _lib.F_NO_SRC_GRAD
         lib = _lib.load()
         dev = tgt.device
-        desc = _lib.make_desc(B, N, S, H, W, flags, alpha, smooth_weight, geo_weight)
-        nbytes = ctypes.c_size_t()
-        _lib.check(lib.colvo_workspace_bytes(ctypes.byref(desc), ctypes.byref(nbytes)), "colvo_workspace_bytes")
+        desc, nbytes, _ = _plan(B, N, S, H, W, flags, alpha, smooth_weight, geo_weight)
         with torch.cuda.device(dev):
-            ws = _Workspace.get(nbytes.value, dev)
+            ws = _Workspace.get(nbytes, dev)
             go = grad_loss.to(torch.float32).contiguous()
             grad_depth = [torch.empty_like(d) for d in depth]
             grad_T = torch.empty_like(pose)
@@ -209,10 +231,12 @@ def photometric_loss(
 
     depth: S tensors `[B,1,H>>k,W>>k]`; pose `[B,N,4,4]` (T target->source); K `[B,3,3]`;
     tgt `[B,3,H,W]`; srcs `[B,N,3,H,W]`.  All CUDA, fp32, contiguous.  Differentiable in
-    depth, pose and srcs; K and tgt get no gradient (oracle A14).
+    depth, pose and srcs; K and tgt get no gradient (oracle A14) and must not require grad.
+    First-order only (`once_differentiable`: a double backward raises instead of returning zeros).
 
     `src_depth [B,N,1,H,W]` (the depth maps of the source frames) with `geo_weight > 0` adds the
     geometric-consistency term of SURVEY.md section 8(f)-2 (oracle A16); it is differentiable too.
+    With `geo_weight == 0` the term is off and `src_depth` is ignored (its gradient is `None`).
 
     Returns the 0-dim loss, or `(loss, valid u8 [B,N,S,H,W], sel u8 [B,S,H,W], ab [B,N,S,2])`.
     """

@@ -5,11 +5,16 @@ from coivo_b200 import _lib
 
 VARIANTS = {
     "base": [],
-    "sm32x16": ["COLVO_SM_BW=32"],
-    "sm64x8": ["COLVO_SM_BH=8"],
-    "sm128x8": ["COLVO_SM_BW=128", "COLVO_SM_BH=8"],
-    "sm32x32": ["COLVO_SM_BW=32", "COLVO_SM_BH=32"],
+    # backward ablations (timing only: these builds give WRONG results and are never loaded by the package)
+    "abl_nored": ["COLVO_EXP_NORED=1"],
+    "abl_nogather": ["COLVO_EXP_NOGATHER=1"],
+    "abl_nobar": ["COLVO_EXP_NOBAR=1"],
 }
+if len(sys.argv) > 1:            # python scripts/build_variants.py name=DEF1,DEF2 ...
+    VARIANTS = {"base": []}
+    for a in sys.argv[1:]:
+        nm, _, defs = a.partition("=")
+        VARIANTS[nm] = [d for d in defs.split(",") if d]
 out = os.path.join(os.path.dirname(_lib.PKG_DIR), "build", "variants")
 os.makedirs(out, exist_ok=True)
 procs = []

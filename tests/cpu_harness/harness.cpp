@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../coivo_b200/csrc/colvo_math.cuh"
+#include "../../coivo_b200/csrc/colvo_pe.cuh"
 
 using namespace colvo;
 
@@ -100,29 +101,44 @@ int harness_run(int B, int N, int S, int H, int W, unsigned flags, const float* 
           moments(tg + (size_t)c * HW, tg + (size_t)c * HW, H, W, px, py, mu, eyy, t2);
           muy[(size_t)c * HW + py * W + px] = mu; sgy[(size_t)c * HW + py * W + px] = eyy - mu * mu;
         }
-    auto pe_image = [&](const float* x, float a, float bb, std::vector<float>& pe, std::vector<float>* dpa, std::vector<float>* dpb) {
+    // photometric error image of one candidate, evaluated as k_photo_fwd does: window SUMS -> colvo_pe.cuh.
+    // cf (optional): the unit-weight SSIM adjoint coefficients of every window, [3][HW]
+    auto pe_image = [&](const float* x, float a, float bb, std::vector<float>& pe, std::vector<float>* dpa, std::vector<float>* dpb,
+                        std::vector<Coef>* cf) {
       pe.assign(HW, 0.f);
       if (dpa) { dpa->assign(HW, 0.f); dpb->assign(HW, 0.f); }
+      if (cf) cf->assign(3 * (size_t)HW, Coef{0, 0, 0});
+      const float a1[1] = {a}, b1[1] = {bb};
+      const CalV<1> cal = make_calv<1>(a1, b1, alpha);
       for (int py = 0; py < H; ++py)
         for (int px = 0; px < W; ++px) {
           int p = py * W + px;
-          float acc = 0, da = 0, db = 0;
+          WinY wy;
+          Vn<1> Sx[3], Sxx[3], Sxy[3], xc[3], ca[3], cb[3], cg[3], da, db;
           for (int c = 0; c < 3; ++c) {
             float mu, exx, exy;
             moments(x + (size_t)c * HW, tg + (size_t)c * HW, H, W, px, py, mu, exx, exy);
-            acc += pe_channel(mu, exx, exy, muy[(size_t)c * HW + p], sgy[(size_t)c * HW + p], x[(size_t)c * HW + p],
-                              tg[(size_t)c * HW + p], a, bb, alpha, c1, c2, dpa ? &da : nullptr, dpa ? &db : nullptr);
+            Sx[c] = Vn<1>(mu * 9.f); Sxx[c] = Vn<1>(exx * 9.f); Sxy[c] = Vn<1>(exy * 9.f);
+            xc[c] = Vn<1>(x[(size_t)c * HW + p]);
+            wy.muy[c] = muy[(size_t)c * HW + p]; wy.sgy[c] = sgy[(size_t)c * HW + p]; wy.yc[c] = tg[(size_t)c * HW + p];
           }
-          pe[p] = acc / 3.f;
-          if (dpa) { (*dpa)[p] = da / 3.f; (*dpb)[p] = db / 3.f; }
+          winy_derive(wy, c1, c2);
+          if (dpa || cf) {
+            pe[p] = pe_fused<1>(Sx, Sxx, Sxy, xc, wy, cal, alpha, c1, c2, ca, cb, cg, da, db).v / 3.f;
+            if (dpa) { (*dpa)[p] = da.v / 3.f; (*dpb)[p] = db.v / 3.f; }
+            if (cf) for (int c = 0; c < 3; ++c) (*cf)[(size_t)c * HW + p] = Coef{ca[c].v, cb[c].v, cg[c].v};
+          } else {
+            pe[p] = pe_value3v<1>(Sx, Sxx, Sxy, xc, wy, cal, alpha, c1, c2).v / 3.f;
+          }
         }
     };
     std::vector<std::vector<float>> ident(N);
-    for (int n = 0; n < N; ++n) pe_image(srcs + ((size_t)b * N + n) * 3 * HW, 1.f, 0.f, ident[n], nullptr, nullptr);
+    for (int n = 0; n < N; ++n) pe_image(srcs + ((size_t)b * N + n) * 3 * HW, 1.f, 0.f, ident[n], nullptr, nullptr, nullptr);
     for (int k = 0; k < S; ++k) {
       const float* Dk = depth[k] + (size_t)b * d.h[k] * d.w[k];
       std::vector<Frame> fr(N);
       std::vector<std::vector<float>> pe(N), dpa(N), dpb(N);
+      std::vector<std::vector<Coef>> cfw(N);
       std::vector<float> a(N, 1.f), bb(N, 0.f);
       std::vector<double> st_n(N, 0), st_mx(N, 0), st_my(N, 0), st_inv(N, 0);
       for (int n = 0; n < N; ++n) {
@@ -145,7 +161,7 @@ int harness_run(int B, int N, int S, int H, int W, unsigned flags, const float* 
         }
         ab_out[(((size_t)b * N + n) * S + k) * 2 + 0] = a[n];
         ab_out[(((size_t)b * N + n) * S + k) * 2 + 1] = bb[n];
-        pe_image(fr[n].x.data(), a[n], bb[n], pe[n], &dpa[n], &dpb[n]);
+        pe_image(fr[n].x.data(), a[n], bb[n], pe[n], &dpa[n], &dpb[n], &cfw[n]);
       }
       std::vector<uint8_t> sel(HW);
       std::vector<double> Ga(N, 0), Gb(N, 0);
@@ -164,19 +180,14 @@ int harness_run(int B, int N, int S, int H, int W, unsigned flags, const float* 
         double ga = Ga[n] * wscale, gb = Gb[n] * wscale;
         float Pc = 0, Qc = 0;
         if (lcc && !detach && st_n[n] > 0) { Pc = (float)((ga - gb * st_mx[n]) * st_inv[n]); Qc = (float)(gb * a[n] / st_n[n]); }
+        // the winner's coefficient fields (unit weight in cfw; the loss weight is applied here), zeros elsewhere
         std::vector<Coef> cf(3 * (size_t)HW);
         for (int c = 0; c < 3; ++c)
-          for (int py = 0; py < H; ++py)
-            for (int px = 0; px < W; ++px) {
-              int p = py * W + px;
-              Coef q = {0, 0, 0};
-              if (sel[p] == N + n) {
-                float mu, exx, exy;
-                moments(fr[n].x.data() + (size_t)c * HW, tg + (size_t)c * HW, H, W, px, py, mu, exx, exy);
-                q = ssim_coef(mu, exx, exy, muy[(size_t)c * HW + p], sgy[(size_t)c * HW + p], a[n], bb[n], alpha, c1, c2, wscale);
-              }
-              cf[(size_t)c * HW + p] = q;
-            }
+          for (int p = 0; p < HW; ++p) {
+            Coef q = {0, 0, 0};
+            if (sel[p] == N + n) { const Coef& u = cfw[n][(size_t)c * HW + p]; q = Coef{u.ca * wscale, u.cb * wscale, u.cg * wscale}; }
+            cf[(size_t)c * HW + p] = q;
+          }
         float gp[12] = {0};
         float* gs = grad_srcs + ((size_t)b * N + n) * 3 * HW;
         for (int py = 0; py < H; ++py)
@@ -242,6 +253,73 @@ int harness_run(int B, int N, int S, int H, int W, unsigned flags, const float* 
     }
   }
   *loss_out = (float)(loss / ((double)S * B * HW));
+  return 0;
+}
+
+
+// The packed two-source window evaluation of the forward tile kernel (colvo_pe.cuh: pe_value3v / pe_fused, lanes =
+// sources) against the scalar per-channel reference (colvo_math.cuh: pe_channel / ssim_coef) on `nw` windows.
+//   x [nw][2][3][9] raw warped taps, y [nw][3][9] target taps (tap 4 = centre), ab [nw][2][2]
+// out_ref / out_new [nw][2][12]: pe, dpa, dpb, (ca, cb, cg) x 3 channels per source; out_one [nw][12]: pe_fused<1> on source 0.
+int harness_pe_fused(int nw, const float* x, const float* y, const float* ab, float alpha, float c1, float c2,
+                     float* out_ref, float* out_new, float* out_one, float* out_val) {
+  for (int i = 0; i < nw; ++i) {
+    const float* xi = x + (size_t)i * 54;
+    const float* yi = y + (size_t)i * 27;
+    WinY wy;
+    float Sxs[2][3], Sxxs[2][3], Sxys[2][3], xcs[2][3];
+    for (int c = 0; c < 3; ++c) {
+      float sy = 0, syy = 0;
+      for (int t = 0; t < 9; ++t) { sy += yi[c * 9 + t]; syy += yi[c * 9 + t] * yi[c * 9 + t]; }
+      wy.muy[c] = sy / 9.f; wy.sgy[c] = syy / 9.f - wy.muy[c] * wy.muy[c]; wy.yc[c] = yi[c * 9 + 4];
+      for (int n = 0; n < 2; ++n) {
+        float s = 0, sxx = 0, sxy = 0;
+        for (int t = 0; t < 9; ++t) { float v = xi[(n * 3 + c) * 9 + t]; s += v; sxx += v * v; sxy += v * yi[c * 9 + t]; }
+        Sxs[n][c] = s; Sxxs[n][c] = sxx; Sxys[n][c] = sxy; xcs[n][c] = xi[(n * 3 + c) * 9 + 4];
+      }
+    }
+    winy_derive(wy, c1, c2);
+    const float a[2] = {ab[i * 4 + 0], ab[i * 4 + 2]}, b[2] = {ab[i * 4 + 1], ab[i * 4 + 3]};
+    // scalar reference
+    for (int n = 0; n < 2; ++n) {
+      float pe = 0, dpa = 0, dpb = 0;
+      float* o = out_ref + ((size_t)i * 2 + n) * 12;
+      for (int c = 0; c < 3; ++c) {
+        Coef cf;
+        pe += pe_channel(Sxs[n][c] / 9.f, Sxxs[n][c] / 9.f, Sxys[n][c] / 9.f, wy.muy[c], wy.sgy[c], xcs[n][c], wy.yc[c], a[n], b[n],
+                         alpha, c1, c2, &dpa, &dpb, true, cf);
+        o[3 + 3 * c] = cf.ca; o[4 + 3 * c] = cf.cb; o[5 + 3 * c] = cf.cg;
+      }
+      o[0] = pe; o[1] = dpa; o[2] = dpb;
+    }
+    // packed: lanes = sources
+    {
+      Vn<2> Sx[3], Sxx[3], Sxy[3], xc[3], ca[3], cb[3], cg[3], dpa, dpb;
+      for (int c = 0; c < 3; ++c) {
+        Sx[c] = Vn<2>(Sxs[0][c], Sxs[1][c]); Sxx[c] = Vn<2>(Sxxs[0][c], Sxxs[1][c]);
+        Sxy[c] = Vn<2>(Sxys[0][c], Sxys[1][c]); xc[c] = Vn<2>(xcs[0][c], xcs[1][c]);
+      }
+      const CalV<2> k = make_calv<2>(a, b, alpha);
+      const Vn<2> pe = pe_fused<2>(Sx, Sxx, Sxy, xc, wy, k, alpha, c1, c2, ca, cb, cg, dpa, dpb);
+      const Vn<2> pv = pe_value3v<2>(Sx, Sxx, Sxy, xc, wy, k, alpha, c1, c2);
+      for (int n = 0; n < 2; ++n) {
+        float* o = out_new + ((size_t)i * 2 + n) * 12;
+        o[0] = pe.lane(n); o[1] = dpa.lane(n); o[2] = dpb.lane(n);
+        for (int c = 0; c < 3; ++c) { o[3 + 3 * c] = ca[c].lane(n); o[4 + 3 * c] = cb[c].lane(n); o[5 + 3 * c] = cg[c].lane(n); }
+        out_val[i * 2 + n] = pv.lane(n);
+      }
+    }
+    {
+      Vn<1> Sx[3], Sxx[3], Sxy[3], xc[3], ca[3], cb[3], cg[3], dpa, dpb;
+      for (int c = 0; c < 3; ++c) { Sx[c] = Vn<1>(Sxs[0][c]); Sxx[c] = Vn<1>(Sxxs[0][c]); Sxy[c] = Vn<1>(Sxys[0][c]); xc[c] = Vn<1>(xcs[0][c]); }
+      const float a1[1] = {a[0]}, b1[1] = {b[0]};
+      const CalV<1> k = make_calv<1>(a1, b1, alpha);
+      const Vn<1> pe = pe_fused<1>(Sx, Sxx, Sxy, xc, wy, k, alpha, c1, c2, ca, cb, cg, dpa, dpb);
+      float* o = out_one + (size_t)i * 12;
+      o[0] = pe.v; o[1] = dpa.v; o[2] = dpb.v;
+      for (int c = 0; c < 3; ++c) { o[3 + 3 * c] = ca[c].v; o[4 + 3 * c] = cb[c].v; o[5 + 3 * c] = cg[c].v; }
+    }
+  }
   return 0;
 }
 

@@ -20,8 +20,8 @@ OUT = os.path.join(HERE, "cpu_harness", "_build", "libharness.so")
 @pytest.fixture(scope="module")
 def harness():
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    hdr = os.path.join(HERE, "..", "coivo_b200", "csrc", "colvo_math.cuh")
-    if not os.path.exists(OUT) or os.path.getmtime(OUT) < max(os.path.getmtime(SRC), os.path.getmtime(hdr)):
+    hdrs = [os.path.join(HERE, "..", "coivo_b200", "csrc", h) for h in ("colvo_math.cuh", "colvo_f2.cuh", "colvo_pe.cuh")]
+    if not os.path.exists(OUT) or os.path.getmtime(OUT) < max([os.path.getmtime(SRC)] + [os.path.getmtime(h) for h in hdrs]):
         subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++", "-std=c++17", SRC, "-o", OUT])
     return ctypes.CDLL(OUT)
 
@@ -82,3 +82,29 @@ def test_harness_matches_oracle(harness, B, H, W, N, S, flags):
     assert relinf(gT[:, :, :3], pose.grad[:, :, :3]) < 1e-4
     assert gT[:, :, 3].abs().max() == 0
     assert relinf(gsrc, srcs.grad) < 1e-4
+
+
+def test_packed_window_evaluation_matches_scalar_reference(harness):
+    """colvo_pe.cuh (what k_photo_fwd runs, sources in the two lanes of a packed register) against the scalar
+    per-channel formulas of colvo_math.cuh, which the test above ties to the oracle's autograd: value, dpe/da, dpe/db
+    and the SSIM adjoint coefficients of both sources, including windows inside and outside the clamp."""
+    g = torch.Generator().manual_seed(3)
+    nw = 4096
+    y = torch.rand(nw, 3, 9, generator=g)
+    x = (y.unsqueeze(1) + 0.2 * torch.randn(nw, 2, 3, 9, generator=g)).contiguous()
+    x[: nw // 8] = 1.0 - y[: nw // 8].unsqueeze(1)            # anti-correlated windows: SSIM < 0, some beyond the clamp
+    x[nw // 8: nw // 4] = x[nw // 8: nw // 4].mean(dim=-1, keepdim=True)   # flat windows: variance ~ 0 against C2
+    ab = torch.stack([0.8 + 0.4 * torch.rand(nw, 2, generator=g), 0.1 * torch.randn(nw, 2, generator=g)], dim=-1).contiguous()
+    ref, new, val = torch.zeros(nw, 2, 12), torch.zeros(nw, 2, 12), torch.zeros(nw, 2)
+    one = torch.zeros(nw, 12)
+    harness.harness_pe_fused.restype = ctypes.c_int
+    rc = harness.harness_pe_fused(ctypes.c_int(nw), ctypes.c_void_p(_fp(x)), ctypes.c_void_p(_fp(y)), ctypes.c_void_p(_fp(ab)),
+                                  ctypes.c_float(0.85), ctypes.c_float(1e-4), ctypes.c_float(9e-4), ctypes.c_void_p(_fp(ref)),
+                                  ctypes.c_void_p(_fp(new)), ctypes.c_void_p(_fp(one)), ctypes.c_void_p(_fp(val)))
+    assert rc == 0
+    # the reference returns pe summed over channels (= 3 pe), dpa / dpb summed over channels, unit-weight coefficients
+    scale = ref.abs().amax(dim=(0, 1))
+    err = (new - ref).abs().amax(dim=(0, 1))
+    assert (err <= 5e-5 * scale + 1e-7).all(), (err / scale)
+    assert torch.allclose(val, new[:, :, 0], rtol=1e-6, atol=1e-7)            # value-only == fused value
+    assert (one - new[:, 0]).abs().max().item() <= 1e-5 * scale.max().item()  # N = 1 instantiation == lane 0 of N = 2
