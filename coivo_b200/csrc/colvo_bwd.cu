@@ -24,8 +24,15 @@
 #ifndef COLVO_EXP_NORED
 #define COLVO_EXP_NORED 0
 #endif
-#ifndef COLVO_BWD_CHAIN_PACKED   // 1: the per-source chain of k_photo_bwd runs both sources in packed fp32x2 lanes (fewer issue
-#define COLVO_BWD_CHAIN_PACKED 1 //    slots, ~127 registers); 0: one source after the other (the gather stays packed either way)
+// Packed fp32x2 in the backward, measured on B200 (profiles/r2_bwd_packed_variants.log): the kernel lives on gather
+// latency at 24 warps / 80 registers per thread, and the packed forms need more live registers than that budget holds
+// (FFMA2 issues at half the FFMA rate, so it saves issue slots, not FMA-pipe time -- scripts/microbench/ffma2_bench.cu):
+//   chain packed + gather packed 241 us,  chain scalar + gather packed 214 us,  both scalar 199 us  <- default
+#ifndef COLVO_BWD_CHAIN_PACKED   // 1: the per-source chain of k_photo_bwd runs both sources in packed fp32x2 lanes; 0: one source
+#define COLVO_BWD_CHAIN_PACKED 0 //    after the other
+#endif
+#ifndef COLVO_BWD_GATHER_PACKED  // 1: one FFMA2 per coefficient feeds both sources' accumulators; 0: scalar FFMA per source
+#define COLVO_BWD_GATHER_PACKED 0
 #endif
 #ifndef COLVO_MINB_BWD      // CTAs per SM the register allocator must allow -- tuned on B200, see DESIGN.md
 #define COLVO_MINB_BWD (24 / COLVO_BWD_TILE_H)     // 24 warps per SM at 80 registers
@@ -218,6 +225,7 @@ __global__ void __launch_bounds__(kBwdThreads, COLVO_MINB_BWD)
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) A[ch] = Bc[ch] = G[ch] = bc<NS>(0.f);
     if (in_img && !COLVO_EXP_NOGATHER) {
+#if COLVO_BWD_GATHER_PACKED
 #pragma unroll
       for (int j = 0; j < 9; ++j) {
         const int o = oc + (j / 3) * kCW + (j % 3);
@@ -233,6 +241,34 @@ __global__ void __launch_bounds__(kBwdThreads, COLVO_MINB_BWD)
           G[ch] = fma2(mn, bc<NS>(q3[ch].z), G[ch]);
         }
       }
+#else
+      float As[NS][3], Bs[NS][3], Gs[NS][3];
+#pragma unroll
+      for (int n = 0; n < NS; ++n)
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) As[n][ch] = Bs[n][ch] = Gs[n][ch] = 0.f;
+#pragma unroll
+      for (int j = 0; j < 9; ++j) {
+        const int o = oc + (j / 3) * kCW + (j % 3);
+        const float m = my3[j / 3] * mx3[j % 3];
+        const float4 q3[3] = {cb[o * 3], cb[o * 3 + 1], cb[o * 3 + 2]};
+        float mn[NS];
+        mn[0] = m * q3[0].w;
+        if (NS > 1) mn[NS - 1] = m * q3[1].w;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+          for (int n = 0; n < NS; ++n) {
+            As[n][ch] = fmaf(mn[n], q3[ch].x, As[n][ch]);
+            Bs[n][ch] = fmaf(mn[n], q3[ch].y, Bs[n][ch]);
+            Gs[n][ch] = fmaf(mn[n], q3[ch].z, Gs[n][ch]);
+          }
+      }
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+        for (int n = 0; n < NS; ++n) { A[ch].set(n, As[n][ch]); Bc[ch].set(n, Bs[n][ch]); G[ch].set(n, Gs[n][ch]); }
+#endif
     }
     mbar_arrive(&mbar[2 + (k & 1)]);          // done reading coefficient buffer k & 1
     float dD = 0.f;

@@ -412,13 +412,14 @@ def photometric_loss(
     return loss, valid_u8, sel_u8, ab
 
 
-def candidate_gap(depth, pose, K, tgt, srcs, *, alpha=ALPHA, lcc=True):
-    """Gap between the two smallest candidates per pixel `[B,S,H,W]` -- the near-tie
-    detector of the `sel` parity protocol (SURVEY.md section 7.4 H2)."""
+def candidates(depth, pose, K, tgt, srcs, *, alpha=ALPHA, lcc=True, ab_override=None):
+    """All 2N candidates of min_reprojection_automask per scale, `[B,S,2N,H,W]`, in the dtype of the inputs (pass
+    float64 tensors for the fp64 adjudication of arg-min near-ties).  `ab_override`
+    `[B,N,S,2]` replaces the calibration values."""
     B, N, S, H, W = _validate(depth, pose, K, tgt, srcs)
     with torch.no_grad():
         ident = [photometric_error(srcs[:, n], tgt, alpha) for n in range(N)]
-        gaps = []
+        out = []
         for k in range(S):
             Dhat = upsample_depth(depth[k], H, W)
             cands = list(ident)
@@ -426,12 +427,34 @@ def candidate_gap(depth, pose, K, tgt, srcs, *, alpha=ALPHA, lcc=True):
                 u, v, valid, _ = reproject(Dhat, K, pose[:, n])
                 Iw = bilinear_sample(srcs[:, n], u, v)
                 if lcc:
-                    a, b = lcc_fit(Iw, tgt, valid)
+                    if ab_override is not None:
+                        a, b = ab_override[:, n, k, 0].to(Iw.dtype), ab_override[:, n, k, 1].to(Iw.dtype)
+                    else:
+                        a, b = lcc_fit(Iw, tgt, valid)
                     Iw = a.reshape(B, 1, 1, 1) * Iw + b.reshape(B, 1, 1, 1)
                 cands.append(photometric_error(Iw, tgt, alpha))
-            two = torch.stack(cands, 1).topk(2, dim=1, largest=False).values
-            gaps.append(two[:, 1] - two[:, 0])
-        return torch.stack(gaps, dim=1)
+            out.append(torch.stack(cands, 1))
+        return torch.stack(out, dim=1)
+
+
+def candidate_gap(depth, pose, K, tgt, srcs, *, alpha=ALPHA, lcc=True):
+    """Gap between the two smallest candidates per pixel `[B,S,H,W]` -- the near-tie
+    detector of the `sel` parity protocol (SURVEY.md section 7.4 H2)."""
+    two = candidates(depth, pose, K, tgt, srcs, alpha=alpha, lcc=lcc).topk(2, dim=2, largest=False).values
+    return two[:, :, 1] - two[:, :, 0]
+
+
+def adjudicate_sel(depth, pose, K, tgt, srcs, sel, ab, *, alpha=ALPHA, lcc=True):
+    """fp64 adjudication of an arg-min decision `sel [B,S,H,W]` made by an fp32 evaluation (the kernel's, or this
+    oracle's own): evaluates every candidate in float64 with the given calibration `ab` and returns
+    `(excess [B,S,H,W] float64, sel64)` where `excess = c64[sel] - min c64 >= 0` is how far the chosen candidate is
+    from the true minimum.  A legitimate near-tie flip has an excess inside the fp32 evaluation noise of pe."""
+    d64 = [x.detach().double() for x in depth]
+    c = candidates(d64, pose.detach().double(), K.double(), tgt.double(), srcs.detach().double(), alpha=alpha, lcc=lcc,
+                   ab_override=ab.double())
+    m, sel64 = c.min(dim=2)
+    chosen = c.gather(2, sel.to(torch.long).unsqueeze(2)).squeeze(2)
+    return chosen - m, sel64.to(torch.uint8)
 
 
 def l1_kink_count(depth, pose, K, tgt, srcs, sel, ab, *, tol: float = 1e-6) -> int:

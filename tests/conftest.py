@@ -24,3 +24,20 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+# Parity statistics the GPU tests want on the record (sel mismatches and their fp64 adjudication, L1 kinks, outlier
+# counts): collected here and printed in the terminal summary, so they show up under -q as well.
+PARITY_STATS = []
+
+
+def record_parity(what, **kw):
+    PARITY_STATS.append((what, kw))
+
+
+def pytest_terminal_summary(terminalreporter):
+    if not PARITY_STATS:
+        return
+    terminalreporter.section("parity statistics (CUDA path vs oracle)")
+    for what, kw in PARITY_STATS:
+        terminalreporter.write_line(what + ": " + ", ".join(f"{k}={v}" for k, v in kw.items()))

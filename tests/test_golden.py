@@ -8,6 +8,7 @@ import pytest
 import torch
 
 from oracle import photometric as O
+from conftest import record_parity
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 FILES = sorted(glob.glob(os.path.join(HERE, "golden", "b*.npz")))
@@ -69,14 +70,28 @@ def test_cuda_path_matches_golden(path):
     loss.backward()
     assert torch.equal(valid.cpu(), t["valid"]), "valid must be bit-exact"
     mism = sel.cpu() != t["sel"]
-    assert (t["gap"][mism] < 1e-4).all()
+    kw = KW.get(name, {})
+    dep = [t[f"depth{k}"] for k in range(S)]
+    # every arg-min mismatch is adjudicated against the candidates evaluated in float64 (tests/test_gpu_parity.py)
+    ex, _ = O.adjudicate_sel(dep, t["pose"], t["K"], t["tgt"], t["srcs"], sel.cpu(), ab.cpu(), lcc=kw.get("lcc", True))
+    assert ex.max().item() <= 5e-5, f"kernel chose a candidate {ex.max().item():.3e} above the fp64 minimum"
     assert abs(loss.item() - t["loss"].item()) <= 1e-4 * abs(t["loss"].item())
     assert torch.allclose(ab.cpu(), t["ab"], rtol=1e-5, atol=1e-6)
-    if not mism.any():       # gradients are comparable only under the same arg-min decisions
-        for k in range(S):
-            assert relinf(depth[k].grad.cpu(), t[f"grad_depth{k}"]) < 1e-4
-        assert relinf(pose.grad.cpu(), t["grad_pose"]) < 1e-4
-        assert relinf(srcs.grad.cpu(), t["grad_srcs"]) < 1e-4
+    ref = {f"grad_depth{k}": t[f"grad_depth{k}"] for k in range(S)}
+    ref["grad_pose"], ref["grad_srcs"] = t["grad_pose"], t["grad_srcs"]
+    if mism.any():
+        # gradients are comparable only under the same arg-min decisions: where the kernel legitimately flipped a
+        # near-tie, the frozen gradients are replaced by the oracle's under the kernel's own decisions (H2 protocol)
+        od = [x.clone().requires_grad_() for x in dep]
+        op, osr = t["pose"].clone().requires_grad_(), t["srcs"].clone().requires_grad_()
+        O.photometric_loss(od, op, t["K"], t["tgt"], osr, sel_override=sel.cpu(), ab_override=ab.cpu(), **kw).backward()
+        ref = {f"grad_depth{k}": od[k].grad for k in range(S)}
+        ref["grad_pose"], ref["grad_srcs"] = op.grad, osr.grad
+    record_parity("golden/" + name, sel_mism=int(mism.sum()), kernel_excess_max=f"{ex.max().item():.2e}")
+    for k in range(S):
+        assert relinf(depth[k].grad.cpu(), ref[f"grad_depth{k}"]) < 1e-4
+    assert relinf(pose.grad.cpu(), ref["grad_pose"]) < 1e-4
+    assert relinf(srcs.grad.cpu(), ref["grad_srcs"]) < 1e-4
 
 
 @pytest.mark.gpu

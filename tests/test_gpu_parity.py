@@ -9,6 +9,7 @@ import torch
 import coivo_b200
 from coivo_b200.synthetic import make_triplets, make_sequence
 from oracle import photometric as O
+from conftest import record_parity
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -21,12 +22,14 @@ def relinf(a, b):
 
 def assert_close_upto_kinks(got, ref, kinks, what, atol=0.0):
     """max-norm parity at TOL, except for at most 8 elements per L1-kink sample (oracle.l1_kink_count: the
-    sample's own depth texel(s) / four bilinear taps), each bounded by 1e-2 of the max.  Strict when kinks == 0."""
+    sample's own depth texel(s) / four bilinear taps), each bounded by 1e-2 of the max.  Strict when kinks == 0.
+    Returns (elements beyond TOL, rel max error) for the record."""
     err = (got - ref).abs()
     scale = ref.abs().max().item()
     bad = err > TOL * scale + atol
     assert int(bad.sum()) <= 8 * kinks, f"{what}: {int(bad.sum())} elements beyond {TOL} (rel {relinf(got, ref)}), {kinks} L1 kinks"
     assert err.max().item() <= 1e-2 * scale + atol, f"{what}: outlier {relinf(got, ref)}"
+    return int(bad.sum()), err.max().item() / max(scale, 1e-30)
 
 
 def run_cuda(d, **kw):
@@ -40,20 +43,39 @@ def run_cuda(d, **kw):
     return loss, valid.cpu(), sel.cpu(), ab.cpu(), [x.grad.cpu() for x in depth], pose.grad.cpu(), srcs.grad.cpu()
 
 
-def check_against_oracle(d, depth_atol=0.0, **kw):
+# SURVEY.md section 7.4 H2 asks for `sel` equal to the oracle's except where the two smallest candidates differ by < 1e-6.
+# That band assumed fp32 evaluations of pe agree to ~1e-7; they do not on flat regions: sigma = E[x^2] - mu^2 carries
+# ~6e-8 absolute rounding against C2 = 9e-4, i.e. up to ~1e-4 relative noise in the SSIM term.  So instead of widening
+# the band on faith, EVERY mismatch is adjudicated against the candidates evaluated in float64: the candidate the kernel
+# chose must lie within SEL_EXCESS of the true (fp64) minimum, and the fp32 oracle's own arg-min is held to the same
+# yardstick and reported next to it (measured: kernel <= 2.6e-5 at 1080x1350, the fp32 oracle itself 2.3e-5 at config 2).
+SEL_EXCESS = 5e-5
+
+
+def adjudicate(d, sel, s0, ab, name, **kw):
+    mism = sel != s0
+    n_mism = int(mism.sum())
+    akw = dict(alpha=kw.get("alpha", 0.85), lcc=kw.get("lcc", True))
+    ex_k, sel64 = O.adjudicate_sel(d["depth"], d["pose"], d["K"], d["tgt"], d["srcs"], sel, ab, **akw)
+    ex_o, _ = O.adjudicate_sel(d["depth"], d["pose"], d["K"], d["tgt"], d["srcs"], s0, ab, **akw)
+    stats = dict(pixels=sel.numel(), sel_mism=n_mism, kernel_vs_fp64=int((sel != sel64).sum()),
+                 oracle32_vs_fp64=int((s0 != sel64).sum()), kernel_excess_max=f"{ex_k.max().item():.2e}",
+                 oracle32_excess_max=f"{ex_o.max().item():.2e}",
+                 mism_beyond_1e6=int((ex_k[mism] > 1e-6).sum()) if n_mism else 0)
+    assert ex_k.max().item() <= SEL_EXCESS, f"{name}: kernel chose a candidate {ex_k.max().item():.3e} above the fp64 minimum"
+    assert mism.float().mean().item() < 1e-3
+    return stats
+
+
+def check_against_oracle(d, depth_atol=0.0, name=None, **kw):
     N, S = d["srcs"].shape[1], len(d["depth"])
+    name = name or f"B{d['tgt'].shape[0]}_{d['tgt'].shape[2]}x{d['tgt'].shape[3]}_N{N}_S{S}" + "".join(f"_{k}={v}" for k, v in kw.items())
     loss, valid, sel, ab, gd, gT, gs = run_cuda(d, **kw)
     with torch.no_grad():
         l0, v0, s0, ab0 = O.photometric_loss(d["depth"], d["pose"], d["K"], d["tgt"], d["srcs"], return_masks=True, **kw)
-        gap = O.candidate_gap(d["depth"], d["pose"], d["K"], d["tgt"], d["srcs"], alpha=kw.get("alpha", 0.85),
-                              lcc=kw.get("lcc", True))
     assert torch.equal(valid, v0), "valid mask must be bit-exact"
     assert torch.allclose(ab, ab0, rtol=1e-5, atol=1e-6)
-    mism = sel != s0
-    # fp32 SSIM: sigma = E[x^2] - mu^2 carries ~6e-8 absolute rounding against C2 = 9e-4, i.e. up to ~1e-4
-    # relative noise in pe on flat regions; a different arg-min is only legitimate inside that band
-    assert (gap[mism] < 1e-4).all(), f"{int(mism.sum())} sel mismatches away from ties"
-    assert mism.float().mean().item() < 1e-3
+    stats = adjudicate(d, sel, s0, ab, name, **kw)
     assert abs(loss.item() - l0.item()) <= TOL * abs(l0.item()), (loss.item(), l0.item())
     od = [x.clone().requires_grad_() for x in d["depth"]]
     op = d["pose"].clone().requires_grad_()
@@ -61,11 +83,16 @@ def check_against_oracle(d, depth_atol=0.0, **kw):
     l1 = O.photometric_loss(od, op, d["K"], d["tgt"], osr, sel_override=sel, ab_override=ab, **kw)
     l1.backward()
     kinks = O.l1_kink_count(d["depth"], d["pose"], d["K"], d["tgt"], d["srcs"], sel, ab) if kw.get("alpha", 0.85) < 1 else 0
+    outliers, worst = 0, 0.0
     for k in range(S):
-        assert_close_upto_kinks(gd[k], od[k].grad, kinks, f"grad_depth[{k}]", depth_atol)
+        n, e = assert_close_upto_kinks(gd[k], od[k].grad, kinks, f"grad_depth[{k}]", depth_atol)
+        outliers += n
+        worst = max(worst, e if depth_atol == 0.0 else 0.0)
     assert relinf(gT[:, :, :3], op.grad[:, :, :3]) < TOL, f"grad_pose {relinf(gT, op.grad)}"
     assert gT[:, :, 3].abs().max().item() == 0
-    assert_close_upto_kinks(gs, osr.grad, kinks, "grad_srcs")
+    n, e = assert_close_upto_kinks(gs, osr.grad, kinks, "grad_srcs")
+    record_parity(name, loss_rel=f"{abs(loss.item() - l0.item()) / abs(l0.item()):.1e}", **stats, l1_kinks=kinks,
+                  grad_outliers=outliers + n, grad_rel_max=f"{max(worst, e, relinf(gT[:, :, :3], op.grad[:, :, :3])):.1e}")
 
 
 @pytest.mark.parametrize("B,H,W,N,S", [
@@ -90,9 +117,19 @@ def test_parity_config2_one_triplet_full_size():
     check_against_oracle(make_triplets(2, 256, 320, seed=0))
 
 
+def test_parity_config2_full_batch():
+    # BASELINE config 2 as it is benchmarked: 12 triplets 256x320, N=2, S=4, every gradient against the oracle
+    check_against_oracle(make_triplets(12, 256, 320, seed=1), name="config2_B12_256x320")
+
+
 def test_parity_highres_slice():
     # BASELINE config 4 geometry (W = 1350 is not a multiple of 4/8/32; pyramid by floor), cropped in H
     check_against_oracle(make_triplets(1, 136, 1350, seed=4))
+
+
+def test_parity_config4_full_resolution():
+    # BASELINE config 4 at its real frame size (1080x1350, pyramid 540x675, 270x337, 135x168 by floor), one triplet
+    check_against_oracle(make_triplets(1, 1080, 1350, seed=4), name="config4_B1_1080x1350")
 
 
 def test_identity_pose_edge_case():
@@ -173,6 +210,21 @@ def test_consistency_sweep_matches_oracle():
     got2 = coivo_b200.consistency(s["depth"].to(DEV), s["pose"].to(DEV), Kp.to(DEV), s["frames"].to(DEV), lcc=False).cpu()
     ref2 = O.consistency(s["depth"], s["pose"], Kp, s["frames"], lcc=False)
     assert torch.allclose(got2, ref2, rtol=1e-4, atol=1e-6)
+
+
+def test_consistency_sweep_config5_frame_size_across_a_pass_boundary():
+    """BASELINE config 5 at its real frame size (256x320), 230 frames: the sweep runs in passes of at most 256 MB of
+    cached warped frames = 195 pairs at this size, so pairs 194 / 195 straddle a pass boundary."""
+    F = 230
+    s = make_sequence(F, 256, 320, seed=7)
+    got = coivo_b200.consistency(s["depth"].to(DEV), s["pose"].to(DEV), s["K"].to(DEV), s["frames"].to(DEV)).cpu()
+    ref = O.consistency(s["depth"], s["pose"], s["K"], s["frames"])
+    assert got.shape == (F - 1, 4)
+    assert torch.equal(got[:, 3], ref[:, 3]), "valid fraction comes from the bit-exact mask"
+    assert torch.allclose(got[:, 1:3], ref[:, 1:3], rtol=1e-5, atol=1e-6)
+    assert torch.allclose(got[:, 0], ref[:, 0], rtol=1e-4, atol=1e-7)
+    record_parity("config5_F230_256x320", pairs=F - 1, pe_rel_max=f"{((got[:, 0] - ref[:, 0]).abs() / ref[:, 0].abs()).max().item():.1e}",
+                  ab_abs_max=f"{(got[:, 1:3] - ref[:, 1:3]).abs().max().item():.1e}")
 
 
 @pytest.mark.parametrize("chunks", [1, 2])
