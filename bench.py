@@ -212,7 +212,7 @@ def run_ours(args):
     t_wall = time.perf_counter()
     e0.record()
     for i in range(steps):
-        lib.colvo_debug_time_kernel(_lib.K_PHOTO_BWD, kev[i][0].cuda_event, kev[i][1].cuda_event)
+        lib.colvo_debug_time_kernel(args.kernel, kev[i][0].cuda_event, kev[i][1].cuda_event)
         step(warmup + i)
     e1.record()
     barrier()
@@ -247,7 +247,7 @@ def run_ours(args):
         if sampler:
             sampler.stop()
         if rank == 0:
-            emit({"profile_run": True, "ms_per_step": ms_total / steps, "kernel_ms": kern_ms})
+            emit({"profile_run": True, "ms_per_step": ms_total / steps, "kernel": args.kernel, "kernel_ms": kern_ms})
         if world > 1:
             dist.destroy_process_group()
         return
@@ -363,6 +363,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--profile", action="store_true", help="profiling run: skip the e2e and CPU-baseline legs")
+    ap.add_argument("--kernel", type=int, default=2, help="which kernel the live event bracket times: 1 k_photo_fwd, 2 k_photo_bwd (default, the dominant one), 3 k_warp_stats")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches only (no CUDA-graph replay leg)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -34,6 +34,15 @@
 #ifndef COLVO_BWD_GATHER_PACKED  // 1: one FFMA2 per coefficient feeds both sources' accumulators; 0: scalar FFMA per source
 #define COLVO_BWD_GATHER_PACKED 0
 #endif
+// Warp-aggregated scatter (north_star: "avoids contended global atomics"): coincident taps of neighbouring pixels are
+// summed inside the warp, through shared-memory exchange slots, before they go to global memory -- two 16-byte REDs per
+// pixel, source and scale instead of four (L2 atomic sectors 68 -> 36 per warp).  Built, parity-green
+// (profiles/r2_scatter_merge.log) and measured SLOWER on B200: 225 us against 199 us for the plain vector-RED scatter
+// (211 vs 203 us at 96 registers): the exchange costs more issue slots and shared-memory bandwidth -- which this kernel
+// is short of -- than the L2 sectors it saves.  Hence a build knob, off by default.
+#ifndef COLVO_BWD_SCATTER_MERGE
+#define COLVO_BWD_SCATTER_MERGE 0
+#endif
 #ifndef COLVO_MINB_BWD      // CTAs per SM the register allocator must allow -- tuned on B200, see DESIGN.md
 #define COLVO_MINB_BWD (24 / COLVO_BWD_TILE_H)     // 24 warps per SM at 80 registers
 #endif
@@ -98,6 +107,8 @@ __global__ void __launch_bounds__(kBwdThreads, COLVO_MINB_BWD)
   unsigned long long* mbar = reinterpret_cast<unsigned long long*>(smem_raw + sizeof(float4) * 2 * kCN * 3 +
                                                                    sizeof(double) * (kBwdThreads / 32) * NS * 12 + 1024);
   static_assert(sizeof(BwdConstV<NS>) * kMaxS + sizeof(V) * 12 + 2 * sizeof(float) <= 1024, "constant area");
+  // scatter exchange slots, [warp][lane][2]: lane l parks its two x1-column taps (value, texel offset) for lane l + 1
+  float4 (*xch)[2] = reinterpret_cast<float4 (*)[2]>(reinterpret_cast<unsigned char*>(mbar) + 64) + (threadIdx.x >> 5) * 32;
 
   pdl_trigger();         // the epilogue launch may become resident while this kernel drains
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
@@ -177,6 +188,10 @@ __global__ void __launch_bounds__(kBwdThreads, COLVO_MINB_BWD)
     }
     mbar_arrive_cp_async(&mbar[k & 1]);      // this thread's share of full[k & 1]
   };
+  // active lanes of a warp are a prefix (one tile row: px grows with the lane); lane 0 has no left neighbour: its slot
+  // keeps a sentinel offset that matches no texel
+  const unsigned amask = __ballot_sync(0xffffffffu, in_img);
+  if (COLVO_BWD_SCATTER_MERGE && tx == 0) xch[0][0] = xch[0][1] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
   if (tid == 0) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) mbar_init(&mbar[i], kBwdThreads);
@@ -349,10 +364,36 @@ __global__ void __launch_bounds__(kBwdThreads, COLVO_MINB_BWD)
             asm volatile("" : "+l"(gs));      // materialised base: one IMAD.WIDE per address (see Img<false>::load_taps)
             const float a00 = w00.lane(i), a01 = w01.lane(i), a10 = w10.lane(i), a11 = w11.lane(i);
             const float h0 = hq[0].lane(i), h1 = hq[1].lane(i), h2 = hq[2].lane(i);
-            red_add3(gs + (unsigned)(r0[i] + t[i].x0), a00 * h0, a00 * h1, a00 * h2);
-            red_add3(gs + (unsigned)(r0[i] + t[i].x1), a01 * h0, a01 * h1, a01 * h2);
-            red_add3(gs + (unsigned)(r1[i] + t[i].x0), a10 * h0, a10 * h1, a10 * h2);
-            red_add3(gs + (unsigned)(r1[i] + t[i].x1), a11 * h0, a11 * h1, a11 * h2);
+            const int o00 = r0[i] + t[i].x0, o01 = r0[i] + t[i].x1, o10 = r1[i] + t[i].x0, o11 = r1[i] + t[i].x1;
+#if COLVO_BWD_SCATTER_MERGE
+            // Warp-aggregated scatter (north_star: no contended global atomics).  Neighbouring pixels of a row sample
+            // neighbouring texels, so the right-hand taps (x1, y0), (x1, y1) of lane l usually ARE the left-hand taps
+            // (x0, y0), (x0, y1) of lane l + 1.  Every lane parks its x1 taps -- three channel values and the texel
+            // offset -- in the slot of its right neighbour, which adds them to its own x0 taps when the offsets agree and
+            // forwards them unchanged when they do not (nothing is lost for any flow field): per pixel, source and
+            // scale two 16-byte REDs leave the SM instead of four.  Shared-memory stores / loads, no shared atomics.
+            const bool has_right = (tx < 31) && ((amask >> (tx + 1)) & 1u);
+            // tap row y0, then tap row y1 (one after the other: fewer live registers; slot [0] / [1] alternate, so one
+            // warp barrier per row also orders the re-use of the other slot)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+              const float ax0 = r ? a10 : a00, ax1 = r ? a11 : a01;
+              const int ox0 = r ? o10 : o00, ox1 = r ? o11 : o01;
+              if (has_right) xch[tx + 1][r] = make_float4(ax1 * h0, ax1 * h1, ax1 * h2, __int_as_float(ox1));
+              __syncwarp(amask);
+              const float4 d = xch[tx][r];
+              const int f = __float_as_int(d.w);
+              const bool m = f == ox0;
+              red_add3(gs + (unsigned)ox0, fmaf(ax0, h0, m ? d.x : 0.f), fmaf(ax0, h1, m ? d.y : 0.f), fmaf(ax0, h2, m ? d.z : 0.f));
+              if (!m && f >= 0) red_add3(gs + (unsigned)f, d.x, d.y, d.z);          // the neighbour's tap lies elsewhere
+              if (!has_right) red_add3(gs + (unsigned)ox1, ax1 * h0, ax1 * h1, ax1 * h2);   // right-most pixel of the row segment
+            }
+#else
+            red_add3(gs + (unsigned)o00, a00 * h0, a00 * h1, a00 * h2);
+            red_add3(gs + (unsigned)o01, a01 * h0, a01 * h1, a01 * h2);
+            red_add3(gs + (unsigned)o10, a10 * h0, a10 * h1, a10 * h2);
+            red_add3(gs + (unsigned)o11, a11 * h0, a11 * h1, a11 * h2);
+#endif
           }
         }
         // geometric consistency (f-2): gradient to Z' directly, to the sampled source depth (scatter) and,
@@ -610,7 +651,8 @@ __global__ void __launch_bounds__(kThreads) k_zero(float4* __restrict__ a, long 
 template <int NS>
 static size_t photo_bwd_smem() {
   return sizeof(float4) * 2 * kCN * 3 + sizeof(double) * (kBwdThreads / 32) * NS * 12 +
-         1024 /* per-frame constants, poses */ + 4 * sizeof(unsigned long long) /* mbarriers */;
+         1024 /* per-frame constants, poses */ + 64 /* mbarriers */ +
+         (COLVO_BWD_SCATTER_MERGE ? sizeof(float4) * 2 * kBwdThreads : 0) /* scatter exchange slots */;
 }
 
 cudaError_t launch_backward(const KP& P, const BwdBuffers& Wk, const float* grad_loss, const uint8_t* sel,

@@ -276,21 +276,21 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_STATS)
       // raw warped frames, re-used by k_photo_fwd instead of warping again (+halo)
       if (iw_a) {
         if constexpr (NS == 1) {
-          iw_a[pix] = make_float4(x[0].lane(0), x[1].lane(0), x[2].lane(0), g.valid[0] ? 1.f : 0.f);
+          st_stream(iw_a + pix, make_float4(x[0].lane(0), x[1].lane(0), x[2].lane(0), g.valid[0] ? 1.f : 0.f));
         } else {
-          iw_a[pix] = make_float4(x[0].lane(0), x[0].lane(1), x[1].lane(0), x[1].lane(1));
-          iw_b2[pix] = make_float2(x[2].lane(0), x[2].lane(1));
+          st_stream(iw_a + pix, make_float4(x[0].lane(0), x[0].lane(1), x[1].lane(0), x[1].lane(1)));
+          st_stream(iw_b2 + pix, make_float2(x[2].lane(0), x[2].lane(1)));
         }
       }
       // the projection itself, for the backward
       if (geo_b) {
         if constexpr (NS == 1) {              // valid rides in the mantissa LSB of the depth
-          geo_b[pix] = make_float4(g.u.lane(0), g.v.lane(0), g.iz.lane(0),
-                                   __uint_as_float((__float_as_uint(D) & ~1u) | (g.valid[0] ? 1u : 0u)));
+          st_stream(geo_b + pix, make_float4(g.u.lane(0), g.v.lane(0), g.iz.lane(0),
+                                             __uint_as_float((__float_as_uint(D) & ~1u) | (g.valid[0] ? 1u : 0u))));
         } else {
-          geo_b[pix] = make_float4(g.u.lane(0), g.u.lane(1), g.v.lane(0), g.v.lane(1));
-          geo_b2[pix] = make_float4(g.iz.lane(0), g.iz.lane(1), D,
-                                    __uint_as_float((g.valid[0] ? 1u : 0u) | (g.valid[NS - 1] ? 2u : 0u)));
+          st_stream(geo_b + pix, make_float4(g.u.lane(0), g.u.lane(1), g.v.lane(0), g.v.lane(1)));
+          st_stream(geo_b2 + pix, make_float4(g.iz.lane(0), g.iz.lane(1), D,
+                                              __uint_as_float((g.valid[0] ? 1u : 0u) | (g.valid[NS - 1] ? 2u : 0u))));
         }
       }
       // LCC products of all sources

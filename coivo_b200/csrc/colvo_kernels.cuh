@@ -169,7 +169,11 @@ template <> struct Img<false> {
     // further plane one more.
     const float* fb = p;
     asm volatile("" : "+l"(fb));
+#ifdef COLVO_EXP_NEARTAPS   // timing ablation (WRONG results): every tap lands in the same 4 KB -> always an L1 hit
+    const unsigned u00 = o00 & 1023, u01 = o01 & 1023, u10 = o10 & 1023, u11 = o11 & 1023, hw = 1024;
+#else
     const unsigned u00 = o00, u01 = o01, u10 = o10, u11 = o11, hw = HW;
+#endif
 #pragma unroll
     for (int c = 0; c < 3; ++c) {       // 32-bit offset add, then one widening multiply-add onto the base
       tx.i00[c] = __ldg(fb + (u00 + c * hw));
@@ -312,6 +316,20 @@ __device__ __forceinline__ void red_add(float* p, float v) {
 // the same for a 16-byte texel (REDG.E.ADD.F32x4): one request for the three channels of a tap
 __device__ __forceinline__ void red_add3(float4* p, float a, float b, float c) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(0.f) : "memory");
+}
+
+// store of an intermediate that a LATER kernel reads.  COLVO_STREAM_STORES = 1: st.global.cs (evict-first) -- the data is
+// not re-read by the writing grid and should not displace the source texels that grid keeps gathering.
+#ifndef COLVO_STREAM_STORES
+#define COLVO_STREAM_STORES 1
+#endif
+template <typename T>
+__device__ __forceinline__ void st_stream(T* p, const T& v) {
+#if COLVO_STREAM_STORES
+  __stcs(p, v);
+#else
+  *p = v;
+#endif
 }
 
 // Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization attribute

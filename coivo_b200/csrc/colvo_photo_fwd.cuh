@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(kFwdThreads, COLVO_MINB_FWD)
                   const float fb = w1 ? cb[c].lane(NS - 1) : cb[c].lane(0);
                   const float fg = w1 ? cg[c].lane(NS - 1) : cg[c].lane(0);
                   const float flag = (c == 0) ? wm.lane(0) : ((c == 1 && NS > 1) ? wm.lane(NS - 1) : 0.f);
-                  co[(long long)c * P.HW] = make_float4(fa, fb, fg, flag);
+                  st_stream(co + (long long)c * P.HW, make_float4(fa, fb, fg, flag));
                 }
               }
             }
