@@ -16,7 +16,8 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 # COLVO_LIB selects another build of the same sources (tuning experiments); the default is the in-tree library
 LIB_PATH = os.environ.get("COLVO_LIB") or os.path.join(PKG_DIR, "libcolvo_b200.so")
 SOURCES = ["colvo_fwd.cu", "colvo_bwd.cu", "colvo_api.cu", "colvo_front.cu"]
-HEADERS = ["colvo_math.cuh", "colvo_kernels.cuh", "colvo_photo_fwd.cuh", os.path.join("..", "..", "include", "colvo.h")]
+HEADERS = ["colvo_math.cuh", "colvo_kernels.cuh", "colvo_photo_fwd.cuh", "colvo_f2.cuh", "colvo_pe.cuh",
+           os.path.join("..", "..", "include", "colvo.h")]
 
 # flags (include/colvo.h)
 F_LCC = 1
@@ -24,6 +25,7 @@ F_LCC_DETACH = 2
 F_SAVE_FOR_BWD = 4
 F_NO_SRC_GRAD = 8
 F_PACKED_BF16 = 16
+F_HOST_U8 = 32
 
 MAX_SCALES = 4
 MAX_SOURCES = 2
@@ -51,6 +53,17 @@ def nvcc_command(out: str = LIB_PATH, defines=()) -> List[str]:
         nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
         "-Xcompiler", "-fPIC", "-shared", "-o", out,
     ] + ["-D" + d for d in defines] + [os.path.join(CSRC, s) for s in SOURCES]
+
+
+def source_hash() -> str:
+    """sha256 (first 16 hex digits) over the kernel sources and headers: ties a profile record (profiles/traffic.json) to
+    the code it was measured on."""
+    import hashlib
+    h = hashlib.sha256()
+    for rel in sorted(SOURCES + HEADERS):
+        with open(os.path.normpath(os.path.join(CSRC, rel)), "rb") as f:
+            h.update(rel.encode() + b"\0" + f.read())
+    return h.hexdigest()[:16]
 
 
 def needs_build() -> bool:
@@ -92,6 +105,8 @@ _SIGS = {
     "colvo_saved_doubles": (ctypes.c_int, [ctypes.POINTER(ColvoDesc), ctypes.POINTER(ctypes.c_size_t)]),
     "colvo_photo_forward": (ctypes.c_int, [ctypes.POINTER(ColvoDesc), _vp, _vp, ctypes.POINTER(_vp), _vp, _vp, _vp, _vp, _vp,
                                            _vp, _vp, _vp, _vp, ctypes.c_size_t, _vp]),
+    "colvo_photo_forward_occ": (ctypes.c_int, [ctypes.POINTER(ColvoDesc), _vp, _vp, ctypes.POINTER(_vp), _vp, _vp, _vp, _vp, _vp,
+                                               _vp, _vp, _vp, _vp, _vp, ctypes.c_size_t, _vp]),
     "colvo_photo_backward": (ctypes.c_int, [ctypes.POINTER(ColvoDesc), _vp, _vp, ctypes.POINTER(_vp), _vp, _vp, _vp, _vp, _vp,
                                             _vp, ctypes.POINTER(_vp), _vp, _vp, _vp, _vp, ctypes.c_size_t, _vp]),
     "colvo_consistency_workspace_bytes": (ctypes.c_int, [ctypes.c_int32] * 3 + [ctypes.POINTER(ctypes.c_size_t)]),
@@ -114,7 +129,7 @@ _SIGS = {
 }
 EXPORTS = tuple(_SIGS)
 
-K_PHOTO_FWD, K_PHOTO_BWD, K_WARP_STATS = 1, 2, 3
+K_PHOTO_FWD, K_PHOTO_BWD, K_WARP_STATS, K_CONSISTENCY_PE = 1, 2, 3, 4
 # kernels launched by one forward + one backward (S > 1, LCC on); bench.py's gpu_launches
 KERNELS_FWD = ("k_warp_stats", "k_lcc_solve", "k_smooth", "k_photo_fwd", "k_smooth", "k_finalize_fwd")   # (k_smooth: two half-batch launches)
 KERNELS_BWD = ("k_zero", "k_photo_bwd", "k_depth_gather")   # (k_depth_gather's launch carries the pose reduction and the unpack)

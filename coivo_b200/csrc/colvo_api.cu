@@ -131,6 +131,17 @@ size_t carve_saved(const ColvoDesc* d, double* saved, SavedView& sv) {
 
 __global__ void k_fill_scalar(float* p, float v) { *p = v; }
 
+// uint8 frames -> fp32 in [0, 1] (COLVO_F_HOST_U8): x = u8 * (1.0f / 255.0f), one rounding; four pixels per thread
+__global__ void __launch_bounds__(256) k_widen_u8(const uint8_t* __restrict__ in, float* __restrict__ out, long long n) {
+  const float s = 1.0f / 255.0f;
+  const long long n4 = n >> 2, stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const uchar4 u = __ldcs(reinterpret_cast<const uchar4*>(in) + i);
+    reinterpret_cast<float4*>(out)[i] = make_float4((float)u.x * s, (float)u.y * s, (float)u.z * s, (float)u.w * s);
+  }
+  for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = (float)in[i] * s;
+}
+
 }  // namespace
 
 extern "C" {
@@ -185,6 +196,13 @@ int colvo_saved_doubles(const ColvoDesc* d, size_t* count) {
 int colvo_photo_forward(const ColvoDesc* d, const void* tgt, const void* srcs, const float* const* depth,
                         const float* K, const float* T, const float* src_depth, float* loss, float* ab,
                         uint8_t* valid, uint8_t* sel, double* saved, void* ws, size_t ws_bytes, void* stream) {
+  return colvo_photo_forward_occ(d, tgt, srcs, depth, K, T, src_depth, loss, ab, valid, sel, nullptr, saved, ws, ws_bytes, stream);
+}
+
+int colvo_photo_forward_occ(const ColvoDesc* d, const void* tgt, const void* srcs, const float* const* depth,
+                            const float* K, const float* T, const float* src_depth, float* loss, float* ab,
+                            uint8_t* valid, uint8_t* sel, float* occ, double* saved, void* ws, size_t ws_bytes,
+                            void* stream) {
   int rc = check_desc(d);
   if (rc) return rc;
   if (!tgt || !srcs || !depth || !K || !T || !loss || !ab || !ws) return COLVO_E_NULL_PTR;
@@ -202,7 +220,8 @@ int colvo_photo_forward(const ColvoDesc* d, const void* tgt, const void* srcs, c
   for (int k = 0; k < d->S; ++k) P.depth[k] = depth[k];
   SavedView sv;
   carve_saved(d, (d->flags & COLVO_F_SAVE_FOR_BWD) ? saved : nullptr, sv);
-  return (int)launch_forward(P, F, loss, ab, valid, sel, sv, static_cast<cudaStream_t>(stream));
+  if (occ && !P.src_depth) return COLVO_E_UNSUPPORTED;     // the occlusion mask is a by-product of the geometric term
+  return (int)launch_forward(P, F, loss, ab, valid, sel, occ, sv, static_cast<cudaStream_t>(stream));
 }
 
 int colvo_photo_backward(const ColvoDesc* d, const void* tgt, const void* srcs, const float* const* depth,
@@ -234,7 +253,7 @@ int colvo_photo_backward(const ColvoDesc* d, const void* tgt, const void* srcs, 
 }
 
 int colvo_debug_time_kernel(int which, void* ev_start, void* ev_stop) {
-  if (which < 0 || which > 3) return COLVO_E_UNSUPPORTED;
+  if (which < 0 || which > 4) return COLVO_E_UNSUPPORTED;
   if (which != 0 && (!ev_start || !ev_stop)) return COLVO_E_NULL_PTR;
   g_timer.which = which;
   g_timer.start = static_cast<cudaEvent_t>(ev_start);
@@ -314,6 +333,7 @@ struct Arena {
   double* saved;
   void* ws;
   size_t ws_bytes;
+  uint8_t *tgt_u8, *srcs_u8;     // byte staging of the frames (COLVO_F_HOST_U8), else null
 };
 
 static size_t carve_arena(const ColvoDesc* d, void* base, Arena& A) {
@@ -336,6 +356,9 @@ static size_t carve_arena(const ColvoDesc* d, void* base, Arena& A) {
   A.saved = c.take<double>(ns);
   colvo_workspace_bytes(d, &A.ws_bytes);
   A.ws = c.take<char>(A.ws_bytes);
+  const bool u8 = (d->flags & COLVO_F_HOST_U8) != 0;       // last, so that the gradient offsets do not depend on the flag
+  A.tgt_u8 = u8 ? c.take<uint8_t>(B * 3 * HW) : nullptr;
+  A.srcs_u8 = u8 ? c.take<uint8_t>(B * N * 3 * HW) : nullptr;
   return c.off;
 }
 
@@ -361,7 +384,7 @@ int colvo_step_host_arena_grads(const ColvoDesc* d, size_t* grad_depth_off, size
   return 0;
 }
 
-int colvo_photo_step_host(const ColvoDesc* d_in, const float* h_tgt, const float* h_srcs, const float* const* h_depth,
+int colvo_photo_step_host(const ColvoDesc* d_in, const void* h_tgt, const void* h_srcs, const float* const* h_depth,
                           const float* h_K, const float* h_T, float* h_loss, float* const* h_grad_depth,
                           float* h_grad_T, float* h_grad_srcs, float grad_scale, void* arena, size_t arena_bytes,
                           void* stream) {
@@ -387,8 +410,17 @@ int colvo_photo_step_host(const ColvoDesc* d_in, const float* h_tgt, const float
     e = cudaMemcpyAsync((dst), (src), sizeof(float) * (count), (kind), st);                 \
     if (e != cudaSuccess) return (int)e;                                                    \
   } while (0)
-  CV_COPY(A.tgt, h_tgt, B * 3 * HW, cudaMemcpyHostToDevice);
-  CV_COPY(A.srcs, h_srcs, B * N * 3 * HW, cudaMemcpyHostToDevice);
+  if (d.flags & COLVO_F_HOST_U8) {      // a quarter of the image bytes over PCIe, widened on the device
+    e = cudaMemcpyAsync(A.tgt_u8, h_tgt, B * 3 * HW, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemcpyAsync(A.srcs_u8, h_srcs, B * N * 3 * HW, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return (int)e;
+    k_widen_u8<<<148 * 4, 256, 0, st>>>(A.tgt_u8, A.tgt, (long long)(B * 3 * HW));
+    k_widen_u8<<<148 * 8, 256, 0, st>>>(A.srcs_u8, A.srcs, (long long)(B * N * 3 * HW));
+  } else {
+    CV_COPY(A.tgt, h_tgt, B * 3 * HW, cudaMemcpyHostToDevice);
+    CV_COPY(A.srcs, h_srcs, B * N * 3 * HW, cudaMemcpyHostToDevice);
+  }
   for (int k = 0; k < d.S; ++k) CV_COPY(A.depth[k], h_depth[k], B * d.h[k] * d.w[k], cudaMemcpyHostToDevice);
   CV_COPY(A.K, h_K, B * 9, cudaMemcpyHostToDevice);
   CV_COPY(A.T, h_T, B * N * 16, cudaMemcpyHostToDevice);
@@ -396,7 +428,7 @@ int colvo_photo_step_host(const ColvoDesc* d_in, const float* h_tgt, const float
   const float* depth_p[kMaxS] = {A.depth[0], A.depth[1], A.depth[2], A.depth[3]};
   float* gdepth_p[kMaxS] = {A.grad_depth[0], A.grad_depth[1], A.grad_depth[2], A.grad_depth[3]};
   d.geo_weight = 0.f;   // the host step carries no source depth maps
-  d.flags &= ~COLVO_F_PACKED_BF16;   // ... and takes planar fp32 images
+  d.flags &= ~(COLVO_F_PACKED_BF16 | COLVO_F_HOST_U8);   // ... and the kernels see planar fp32 images
   rc = colvo_photo_forward(&d, A.tgt, A.srcs, depth_p, A.K, A.T, nullptr, A.loss, A.ab, nullptr, A.sel, A.saved, A.ws,
                            A.ws_bytes, stream);
   if (rc) return rc;

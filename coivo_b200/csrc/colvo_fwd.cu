@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(kThreads)
 template <int NS, bool GEO, bool PK>
 __global__ void __launch_bounds__(kThreads, COLVO_MINB_STATS)
     k_warp_stats(KP P, double* __restrict__ part, uint8_t* __restrict__ valid_out, float4* __restrict__ iw_out,
-                 float4* __restrict__ geo_out) {
+                 float4* __restrict__ geo_out, float* __restrict__ occ_out) {
   constexpr int NA = GEO ? kStatVals : 5;      // accumulators per source (the 6th only with the geometric term)
   constexpr int NV = NA * NS;
   typedef Vn<NS> V;
@@ -219,6 +219,7 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_STATS)
   const unsigned out_nstride = (unsigned)P.S * (unsigned)P.HW, hw = P.HW;
   const long long out_bk = (long long)(b * P.N * P.S + k) * P.HW;
   uint8_t* valid_b = valid_out ? valid_out + out_bk : nullptr;
+  float* occ_b = (GEO && occ_out) ? occ_out + out_bk : nullptr;     // soft occlusion mask 1 - diff (0 where invalid), [B,N,S,H,W]
   // saved projection: N = 1 one texel array; N = 2 the planes A = (u^0, u^1, v^0, v^1) and B = (iz^0, iz^1, D^, valid bits)
   float4* geo_b = geo_out ? geo_out + (long long)(b * P.S + k) * P.HW : nullptr;
   float4* geo_b2 = (geo_out && NS == 2) ? geo_out + (long long)((P.B + b) * P.S + k) * P.HW : nullptr;
@@ -302,6 +303,7 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_STATS)
       for (int n = 0; n < NS; ++n) {
         const unsigned opix = (unsigned)pix + n * out_nstride;
         if (valid_b) valid_b[opix] = g.valid[n] ? 1 : 0;
+        float occ = 0.f;
         if (g.valid[n]) {
           acc[NA * n + 0] += 3.0;
           acc[NA * n + 1] += (double)s1.lane(n);
@@ -311,9 +313,12 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_STATS)
           if (GEO) {               // geometric consistency (f-2): per-pixel, so it lives in this pass
             float d4[4], dZ, dS;
             const float ds = sample_plane(P.src_depth + (long long)(b * P.N + n) * P.HW, t[n], P.W, d4);
-            acc[NA * n + (NA - 1)] += (double)geo_diff(g.Zp.lane(n), ds, dZ, dS);
+            const float diff = geo_diff(g.Zp.lane(n), ds, dZ, dS);
+            acc[NA * n + (NA - 1)] += (double)diff;
+            occ = 1.0f - diff;
           }
         }
+        if (GEO && occ_b) occ_b[opix] = occ;
       }
     }
     pix += kThreads;
@@ -605,7 +610,7 @@ __global__ void __launch_bounds__(kThreads)
 
 // ------------------------------------------------------------------------------------------
 cudaError_t launch_forward(const KP& P, const FwdBuffers& Wk, float* loss, float* ab, uint8_t* valid, uint8_t* sel,
-                           const SavedView& sv, cudaStream_t st) {
+                           float* occ, const SavedView& sv, cudaStream_t st) {
   const bool lcc = (P.flags & 1u) != 0;
   const bool save = (P.flags & 4u) != 0;
   const int need_g = (save && lcc && !(P.flags & 2u)) ? 1 : 0;
@@ -615,7 +620,7 @@ cudaError_t launch_forward(const KP& P, const FwdBuffers& Wk, float* loss, float
     ScopedKernelTimer tm(3, st);
     dim3 g(Wk.stat_chunks, P.B * P.S);
     const bool geo = P.src_depth != nullptr;
-    auto run = [&](auto kern) { kern<<<g, kThreads, 0, st>>>(P, Wk.stat_part, valid, Wk.iw, save ? sv.geo : nullptr); };
+    auto run = [&](auto kern) { kern<<<g, kThreads, 0, st>>>(P, Wk.stat_part, valid, Wk.iw, save ? sv.geo : nullptr, occ); };
     if (P.N == 1) {
       if (geo) { if (pk) run(k_warp_stats<1, true, true>); else run(k_warp_stats<1, true, false>); }
       else { if (pk) run(k_warp_stats<1, false, true>); else run(k_warp_stats<1, false, false>); }
@@ -689,9 +694,15 @@ cudaError_t launch_consistency(const KP& P0, double* stat_part, int stat_chunks,
     P.T = P0.T + (long long)p0 * P0.T_bs;
     double* sp = stat_part + (long long)p0 * stat_chunks * kStatVals;
     float* abp = ab + 2 * p0;
-    k_warp_stats<1, false, false><<<dim3(stat_chunks, P.B), kThreads, 0, st>>>(P, sp, nullptr, iw, nullptr);
+    {
+      ScopedKernelTimer tm(3, st);
+      k_warp_stats<1, false, false><<<dim3(stat_chunks, P.B), kThreads, 0, st>>>(P, sp, nullptr, iw, nullptr, nullptr);
+    }
     k_lcc_solve<<<P.B, 32, 0, st>>>(P, sp, stat_chunks, abp, nullptr);
-    k_consistency_pe<<<dim3(P.ftiles_x, P.ftiles_y, P.B), kFwdThreads, 0, st>>>(P, abp, iw, pe_part + (long long)p0 * tiles * 2);
+    {
+      ScopedKernelTimer tm(4, st);
+      k_consistency_pe<<<dim3(P.ftiles_x, P.ftiles_y, P.B), kFwdThreads, 0, st>>>(P, abp, iw, pe_part + (long long)p0 * tiles * 2);
+    }
   }
   k_consistency_final<<<P0.B, kThreads, 0, st>>>(P0, pe_part, ab, out);
   return cudaGetLastError();

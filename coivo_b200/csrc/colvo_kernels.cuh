@@ -448,7 +448,7 @@ struct ScopedKernelTimer {
 };
 
 cudaError_t launch_forward(const KP& P, const FwdBuffers& W, float* loss, float* ab, uint8_t* valid, uint8_t* sel,
-                           const SavedView& saved, cudaStream_t st);
+                           float* occ, const SavedView& saved, cudaStream_t st);
 cudaError_t launch_backward(const KP& P, const BwdBuffers& W, const float* grad_loss, const uint8_t* sel,
                             const SavedView& saved, float* const* grad_depth, float* grad_T, float* grad_srcs,
                             float* grad_src_depth, cudaStream_t st);

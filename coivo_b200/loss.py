@@ -126,6 +126,8 @@ def _plan(B, N, S, H, W, flags, alpha, smooth_weight, geo_weight):
 class _PhotoLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pose, K, tgt, srcs, alpha, smooth_weight, lcc, lcc_detach, want_valid, src_depth, geo_weight, *depth):
+        want_occ = want_valid == 2            # 2: masks and the soft occlusion mask of the geometric term
+        want_valid = bool(want_valid)
         B, N, S, H, W, packed = _check_inputs(depth, pose, K, tgt, srcs)
         if src_depth is not None:
             if tuple(src_depth.shape) != (B, N, 1, H, W):
@@ -138,6 +140,8 @@ class _PhotoLossFn(torch.autograd.Function):
             geo_weight = 0.0
         if geo_weight == 0.0:
             src_depth = None          # the term is off: the source depth maps take no part (and get no gradient)
+        if want_occ and src_depth is None:
+            raise ValueError("return_occlusion needs src_depth and geo_weight != 0 (the mask is a by-product of that term)")
         if K.requires_grad or tgt.requires_grad:
             raise ValueError("photometric_loss gives no gradient to K or tgt (oracle A14): detach them")
         lib = _lib.load()
@@ -155,11 +159,13 @@ class _PhotoLossFn(torch.autograd.Function):
             # forward -> backward state: only when a backward can follow (validation / no_grad allocates nothing)
             saved = torch.empty(nsaved, dtype=torch.float64, device=dev) if needs_grad else None
             valid = torch.empty(B, N, S, H, W, dtype=torch.uint8, device=dev) if want_valid else None
+            occ = torch.empty(B, N, S, H, W, dtype=torch.float32, device=dev) if want_occ else None
             stream = torch.cuda.current_stream(dev).cuda_stream
-            rc = lib.colvo_photo_forward(
+            rc = lib.colvo_photo_forward_occ(
                 ctypes.byref(desc), tgt.data_ptr(), srcs.data_ptr(), _lib.ptr_array([d.data_ptr() for d in depth]),
                 K.data_ptr(), pose.data_ptr(), src_depth.data_ptr() if src_depth is not None else None, loss.data_ptr(),
                 ab.data_ptr(), valid.data_ptr() if valid is not None else None, sel.data_ptr(),
+                occ.data_ptr() if occ is not None else None,
                 saved.data_ptr() if saved is not None else None, ws.data_ptr(), ws.numel(), stream)
         _lib.check(rc, "colvo_photo_forward")
         ctx.desc_args = (B, N, S, H, W, flags, alpha, smooth_weight, geo_weight)
@@ -170,6 +176,9 @@ class _PhotoLossFn(torch.autograd.Function):
             ctx.save_for_backward(pose, K, tgt, srcs, sel, saved, *extra, *depth)
         ctx.mark_non_differentiable(ab, sel)
         ctx.set_materialize_grads(False)      # no zero-filled "gradients" for the mask outputs (a 4 MB fill per step)
+        if occ is not None:
+            ctx.mark_non_differentiable(valid, occ)
+            return loss, ab, sel, valid, occ
         if valid is not None:
             ctx.mark_non_differentiable(valid)
             return loss, ab, sel, valid
@@ -225,6 +234,7 @@ def photometric_loss(
     return_masks: bool = False,
     src_depth: Optional[torch.Tensor] = None,
     geo_weight: float = 0.0,
+    return_occlusion: bool = False,
 ):
     """View-synthesis photometric loss with LCC, min-reprojection / auto-mask and edge-aware
     smoothness over S scales and N neighbouring frames.
@@ -238,10 +248,15 @@ def photometric_loss(
     geometric-consistency term of SURVEY.md section 8(f)-2 (oracle A16); it is differentiable too.
     With `geo_weight == 0` the term is off and `src_depth` is ignored (its gradient is `None`).
 
-    Returns the 0-dim loss, or `(loss, valid u8 [B,N,S,H,W], sel u8 [B,S,H,W], ab [B,N,S,2])`.
+    Returns the 0-dim loss, or `(loss, valid u8 [B,N,S,H,W], sel u8 [B,S,H,W], ab [B,N,S,2])`; with
+    `return_occlusion=True` (needs the geometric term) a fifth item `occ [B,N,S,H,W]`: SC-Depth's soft occlusion mask
+    `1 - diff` (0 where the projection is invalid), a constant by-product of that term.
     """
     out = _PhotoLossFn.apply(pose, K, tgt, srcs, float(alpha), float(smooth_weight), bool(lcc), bool(lcc_detach),
-                             bool(return_masks), src_depth, float(geo_weight), *depth)
+                             2 if return_occlusion else int(bool(return_masks)), src_depth, float(geo_weight), *depth)
+    if return_occlusion:
+        loss, ab, sel, valid, occ = out
+        return loss, valid, sel, ab, occ
     if return_masks:
         loss, ab, sel, valid = out
         return loss, valid, sel, ab
@@ -260,12 +275,18 @@ class HostStepper:
 
     `grads="host"` copies every gradient back to pinned host buffers; `grads="device"` leaves them in
     the device arenas (what a training step does: the depth / pose networks consume them on the GPU)
-    and reads back the loss only -- `device_grads()` returns views of them."""
+    and reads back the loss only -- `device_grads()` returns views of them.
+
+    `images="u8"`: `tgt` / `srcs` are uint8 frames (what a video loader holds); they cross PCIe as bytes -- a quarter of
+    the image traffic of the H2D-bound step -- and are widened on the device, `x = u8 * (1 / 255)` in fp32."""
 
     def __init__(self, B, N, S, H, W, *, device="cuda:0", lcc=True, lcc_detach=False, want_src_grad=True,
-                 alpha=0.85, smooth_weight=1e-3, chunks=None, grads="host"):
+                 alpha=0.85, smooth_weight=1e-3, chunks=None, grads="host", images="f32"):
         if grads not in ("host", "device"):
             raise ValueError("grads must be 'host' or 'device'")
+        if images not in ("f32", "u8"):
+            raise ValueError("images must be 'f32' or 'u8'")
+        self.images = images
         if chunks is None:       # measured on B200 / PCIe 5 (scripts/e2e_chunks.py): two streams keep the H2D engine busy
             chunks = 3 if grads == "host" else 2     # when only the loss comes back, three also overlap the gradient D2H
         self.grads = grads
@@ -275,6 +296,8 @@ class HostStepper:
         flags = (_lib.F_LCC if lcc else 0) | (_lib.F_LCC_DETACH if lcc_detach else 0)
         if not want_src_grad:
             flags |= _lib.F_NO_SRC_GRAD
+        if images == "u8":         # frames cross PCIe as bytes and are widened on the device: x = u8 * (1 / 255)
+            flags |= _lib.F_HOST_U8
         chunks = max(1, min(int(chunks), B))
         q, r = divmod(B, chunks)
         sizes = [q + (1 if i < r else 0) for i in range(chunks)]
@@ -300,7 +323,8 @@ class HostStepper:
         self._done = [torch.cuda.Event() for _ in sizes]
 
     def h2d_bytes(self, depth, pose, K, tgt, srcs) -> int:
-        return 4 * (tgt.numel() + srcs.numel() + sum(d.numel() for d in depth) + K.numel() + pose.numel())
+        return (tgt.numel() * tgt.element_size() + srcs.numel() * srcs.element_size()
+                + 4 * (sum(d.numel() for d in depth) + K.numel() + pose.numel()))
 
     def d2h_bytes(self) -> int:
         n = len(self.spans)
@@ -336,9 +360,10 @@ class HostStepper:
     def step(self, depth, pose, K, tgt, srcs):
         """Inputs are CPU tensors (pinned for full speed).  Enqueues every chunk on its own stream, ordered
         after the caller's current stream; call `finish()` (or synchronise) before reading the host outputs."""
-        for t in list(depth) + [pose, K, tgt, srcs]:
-            if t.device.type != "cpu" or t.dtype != torch.float32 or not t.is_contiguous():
-                raise ValueError("HostStepper.step takes contiguous float32 CPU tensors")
+        img_dtype = torch.uint8 if self.images == "u8" else torch.float32
+        for t, dt in [(x, torch.float32) for x in list(depth) + [pose, K]] + [(tgt, img_dtype), (srcs, img_dtype)]:
+            if t.device.type != "cpu" or t.dtype != dt or not t.is_contiguous():
+                raise ValueError("HostStepper.step takes contiguous CPU tensors: float32, and uint8 frames with images='u8'")
         cur = torch.cuda.current_stream(self.device)
         with torch.cuda.device(self.device):
             for i, (lo, hi) in enumerate(self.spans):

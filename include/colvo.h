@@ -43,6 +43,9 @@ extern "C" {
                                       arithmetic stays fp32; requires COLVO_F_NO_SRC_GRAD in the backward
                                                                         */
 
+#define COLVO_F_HOST_U8 32u        /* colvo_photo_step_host only: h_tgt / h_srcs are uint8 frames (what a video loader holds);
+                                      they are copied as bytes and widened on the device, x = u8 * (1.0f / 255.0f)   */
+
 /* negative error codes */
 #define COLVO_E_BAD_DESC (-1)
 #define COLVO_E_WORKSPACE (-2)
@@ -92,6 +95,17 @@ int colvo_photo_forward(const ColvoDesc* d, const void* tgt, const void* srcs, c
                         const float* K, const float* T, const float* src_depth, float* loss, float* ab,
                         uint8_t* valid, uint8_t* sel, double* saved, void* ws, size_t ws_bytes, void* stream);
 
+/* The same forward with one more output (SURVEY.md section 8(f)-2 "also yields a soft occlusion mask"):
+ *   occ [B,N,S,H,W] fp32  (out, nullable)  1 - diff of the geometric-consistency term where the projection is valid, 0
+ *                         elsewhere (SC-Depth's weight mask: small where the re-projected depth disagrees with the
+ *                         source frame's own depth map, i.e. at occlusions / moving tissue).  Needs src_depth and
+ *                         geo_weight != 0 (COLVO_E_UNSUPPORTED otherwise); a constant, no gradient flows through it.
+ */
+int colvo_photo_forward_occ(const ColvoDesc* d, const void* tgt, const void* srcs, const float* const* depth,
+                            const float* K, const float* T, const float* src_depth, float* loss, float* ab,
+                            uint8_t* valid, uint8_t* sel, float* occ, double* saved, void* ws, size_t ws_bytes,
+                            void* stream);
+
 /* Backward: SURVEY.md section 8(a) row 11.  Inputs as in the forward plus its sel / saved.
  *   grad_loss  [1] device scalar (dL_total / dloss)
  *   grad_depth[k] [B,1,h_k,w_k]   (out, overwritten)
@@ -125,10 +139,12 @@ int colvo_consistency(int32_t F, int32_t H, int32_t W, uint32_t flags, const flo
  * outputs are complete once `stream` has been synchronised.  A caller that splits a batch into
  * chunks on several streams (to overlap H2D, compute and D2H) passes grad_scale = B_chunk / B and
  * combines the chunk losses with the same weights.
+ * h_tgt [B,3,H,W] / h_srcs [B,N,3,H,W] are fp32, or uint8 with COLVO_F_HOST_U8 (a quarter of the image bytes cross
+ * PCIe; the arena then also holds the byte staging area).
  */
 int colvo_step_host_arena_bytes(const ColvoDesc* d, size_t* bytes);
 int colvo_step_host_arena_grads(const ColvoDesc* d, size_t* grad_depth_off, size_t* grad_T_off, size_t* grad_srcs_off);
-int colvo_photo_step_host(const ColvoDesc* d, const float* h_tgt, const float* h_srcs, const float* const* h_depth,
+int colvo_photo_step_host(const ColvoDesc* d, const void* h_tgt, const void* h_srcs, const float* const* h_depth,
                           const float* h_K, const float* h_T, float* h_loss, float* const* h_grad_depth,
                           float* h_grad_T, float* h_grad_srcs, float grad_scale, void* arena, size_t arena_bytes,
                           void* stream);
@@ -154,10 +170,11 @@ int colvo_disp_to_depth_backward(int32_t S, const int64_t* counts, const float* 
 /* Profiling aid (bench.py's roofline leg): bracket the NEXT launch of one kernel with two
  * caller-owned cudaEvent_t on the launching stream.  One-shot, process-wide; pass
  * which = 0 to clear.  Not for use under CUDA-graph capture.
- *   which: 1 = k_photo_fwd, 2 = k_photo_bwd, 3 = k_warp_stats */
+ *   which: 1 = k_photo_fwd, 2 = k_photo_bwd, 3 = k_warp_stats, 4 = k_consistency_pe (first pass of a sweep) */
 #define COLVO_K_PHOTO_FWD 1
 #define COLVO_K_PHOTO_BWD 2
 #define COLVO_K_WARP_STATS 3
+#define COLVO_K_CONSISTENCY_PE 4
 int colvo_debug_time_kernel(int which, void* ev_start, void* ev_stop);
 
 #ifdef __cplusplus

@@ -285,10 +285,15 @@ def geometric_consistency(Zp: torch.Tensor, src_depth_n: torch.Tensor, u: torch.
 
     `Zp, u, v, valid [B,H,W]`, `src_depth_n [B,1,H,W]` -> scalar.  Differentiable in the target depth and
     the pose (through Z', u', v') and in the source depth map; the mask is a constant."""
+    return geometric_diff(Zp, src_depth_n, u, v, valid).mean()
+
+
+def geometric_diff(Zp, src_depth_n, u, v, valid):
+    """Per-pixel `diff` of `geometric_consistency` (0 where invalid), `[B,H,W]`.  `where(valid, 1 - diff, 0)` is
+    SC-Depth's soft occlusion / weight mask (SURVEY.md section 8(f)-2 "also yields a soft occlusion mask")."""
     Ds = bilinear_sample(src_depth_n, u, v)[:, 0]
     diff = torch.clamp((Zp - Ds).abs() / (Zp + Ds), 0, 1)
-    diff = torch.where(valid, diff, torch.zeros_like(diff))
-    return diff.mean()
+    return torch.where(valid, diff, torch.zeros_like(diff))
 
 
 # --------------------------------------------------------------------------------------
@@ -343,6 +348,7 @@ def photometric_loss(
     ab_override: Optional[torch.Tensor] = None,
     src_depth: Optional[torch.Tensor] = None,
     geo_weight: float = 0.0,
+    return_occlusion: bool = False,
 ):
     """The oracle for SURVEY.md section 8(a) rows 0-10 (row 11 = autograd of this).
 
@@ -357,7 +363,9 @@ def photometric_loss(
     (SURVEY.md section 7.4 H2).
 
     `src_depth [B,N,1,H,W]` with `geo_weight > 0` adds the geometric-consistency term of
-    SURVEY.md section 8(f)-2 (see `geometric_consistency`), per scale, with the same 1/S.
+    SURVEY.md section 8(f)-2 (see `geometric_consistency`), per scale, with the same 1/S;
+    `return_occlusion=True` then appends `occ [B,N,S,H,W]`, the soft occlusion mask `valid ? 1 - diff : 0`
+    (a detached by-product, see `geometric_diff`) to the returned tuple.
     """
     B, N, S, H, W = _validate(depth, pose, K, tgt, srcs)
     tgt_c = tgt.detach()
@@ -368,7 +376,9 @@ def photometric_loss(
     ident = [photometric_error(srcs[:, n].detach(), tgt_c, alpha) for n in range(N)]
     pyr = target_pyramid(tgt_c, S)
     total = tgt.new_zeros(())
-    valids, sels, abs_ = [], [], []
+    if return_occlusion and not geo_on:
+        raise ValueError("return_occlusion needs src_depth and geo_weight != 0")
+    valids, sels, abs_, occs = [], [], [], []
     for k in range(S):
         Dhat = upsample_depth(depth[k], H, W)
         cands = list(ident)
@@ -378,7 +388,9 @@ def photometric_loss(
             u, v, valid, Zp = reproject(Dhat, K, pose[:, n])
             Iw = bilinear_sample(srcs[:, n], u, v)
             if geo_on:
-                l_geo = l_geo + geometric_consistency(Zp, src_depth[:, n], u, v, valid) / N
+                diff = geometric_diff(Zp, src_depth[:, n], u, v, valid)
+                l_geo = l_geo + diff.mean() / N
+                occs.append(torch.where(valid, 1.0 - diff.detach(), torch.zeros_like(diff)))
             if lcc:
                 a, b = lcc_fit(Iw.detach() if lcc_detach else Iw, tgt_c, valid)
                 if ab_override is not None:
@@ -404,11 +416,14 @@ def photometric_loss(
         sels.append(sel)
         abs_.append(torch.stack(ab_k, dim=1))                 # [B,N,2]
     loss = total / S
-    if not return_masks:
+    if not (return_masks or return_occlusion):
         return loss
     valid_u8 = torch.stack(valids, dim=2).to(torch.uint8)     # [B,N,S,H,W]
     sel_u8 = torch.stack(sels, dim=1).to(torch.uint8)         # [B,S,H,W]
     ab = torch.stack(abs_, dim=2).detach()                    # [B,N,S,2]
+    if return_occlusion:                                      # occs is ordered (k, n) -> [B,N,S,H,W]
+        occ = torch.stack(occs, dim=1).reshape(B, S, N, H, W).transpose(1, 2).contiguous()
+        return loss, valid_u8, sel_u8, ab, occ
     return loss, valid_u8, sel_u8, ab
 
 

@@ -258,6 +258,29 @@ def test_host_stepper_matches_device_path(chunks):
     assert st.d2h_bytes() == 4 * (chunks + sum(x.numel() for x in gd) + gT.numel() + gs.numel())
 
 
+def test_host_stepper_uint8_frames():
+    """COLVO_F_HOST_U8: uint8 frames widened on the device, x = u8 * (1/255) -- bit-identical to the fp32 step on the
+    same widened values."""
+    d = make_triplets(3, 37, 53, seed=17)             # ragged size: the scalar tail of the widening kernel is exercised
+    to_u8 = lambda t: (t * 255.0).round().clamp_(0, 255).to(torch.uint8)
+    tgt8, srcs8 = to_u8(d["tgt"]), to_u8(d["srcs"])
+    c = torch.tensor(1.0 / 255.0, dtype=torch.float32)
+    d["tgt"], d["srcs"] = tgt8.float() * c, srcs8.float() * c
+    pin = lambda t: t.pin_memory()
+    st = coivo_b200.HostStepper(3, 2, 4, 37, 53, device=DEV, chunks=1, images="u8")
+    st.step([pin(x) for x in d["depth"]], pin(d["pose"]), pin(d["K"]), pin(tgt8), pin(srcs8))
+    h = st.finish()
+    loss, valid, sel, ab, gd, gT, gs = run_cuda(d)
+    assert h.item() == loss.item()
+    for k in range(4):
+        assert torch.equal(st.h_grad_depth[k], gd[k])
+    assert torch.equal(st.h_grad_T, gT)
+    assert relinf(st.h_grad_srcs, gs) < 1e-5
+    assert st.h2d_bytes([pin(x) for x in d["depth"]], d["pose"], d["K"], tgt8, srcs8) < 0.4 * st.h2d_bytes(d["depth"], d["pose"], d["K"], d["tgt"], d["srcs"])
+    with pytest.raises(ValueError):
+        st.step(d["depth"], d["pose"], d["K"], d["tgt"], d["srcs"])      # float frames into a uint8 stepper
+
+
 def test_graphed_step_replays_the_eager_result():
     d = make_triplets(2, 64, 96, seed=15)
     mk = lambda: ([x.to(DEV).requires_grad_() for x in d["depth"]], d["pose"].to(DEV).requires_grad_(),
@@ -292,8 +315,8 @@ def test_geometric_consistency_term_parity(B, H, W, N, S):
     pose = d["pose"].to(DEV).requires_grad_()
     srcs = d["srcs"].to(DEV).requires_grad_()
     sdg = sd.to(DEV).requires_grad_()
-    loss, valid, sel, ab = coivo_b200.photometric_loss(depth, pose, d["K"].to(DEV), d["tgt"].to(DEV), srcs,
-                                                       src_depth=sdg, geo_weight=0.5, return_masks=True)
+    loss, valid, sel, ab, occ = coivo_b200.photometric_loss(depth, pose, d["K"].to(DEV), d["tgt"].to(DEV), srcs,
+                                                            src_depth=sdg, geo_weight=0.5, return_occlusion=True)
     loss.backward()
     with torch.no_grad():
         l_plain = coivo_b200.photometric_loss([x.detach() for x in depth], pose.detach(), d["K"].to(DEV), d["tgt"].to(DEV),
@@ -303,9 +326,16 @@ def test_geometric_consistency_term_parity(B, H, W, N, S):
     op = d["pose"].clone().requires_grad_()
     osr = d["srcs"].clone().requires_grad_()
     osd = sd.clone().requires_grad_()
-    l_ref = O.photometric_loss(od, op, d["K"], d["tgt"], osr, src_depth=osd, geo_weight=0.5, sel_override=sel.cpu(),
-                               ab_override=ab.cpu())
+    l_ref, v_ref, _, _, occ_ref = O.photometric_loss(od, op, d["K"], d["tgt"], osr, src_depth=osd, geo_weight=0.5,
+                                                     sel_override=sel.cpu(), ab_override=ab.cpu(), return_occlusion=True)
     l_ref.backward()
+    # the soft occlusion mask (SC-Depth's 1 - diff; 0 where invalid): a constant by-product of the term
+    assert torch.equal(valid.cpu(), v_ref)
+    assert occ.shape == (B, N, S, H, W) and not occ.requires_grad
+    assert (occ.cpu() - occ_ref).abs().max().item() <= 1e-6
+    assert torch.equal(occ.cpu() == 0, (v_ref == 0) | (occ_ref == 0))
+    with pytest.raises(ValueError):
+        coivo_b200.photometric_loss(depth, pose, d["K"].to(DEV), d["tgt"].to(DEV), srcs, return_occlusion=True)
     assert abs(loss.item() - l_ref.item()) <= TOL * abs(l_ref.item())
     for k in range(S):
         assert relinf(depth[k].grad, od[k].grad) < TOL, f"grad_depth[{k}]"
