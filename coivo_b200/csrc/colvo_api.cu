@@ -11,6 +11,27 @@ using namespace colvo;
 
 namespace colvo {
 KernelTimer g_timer = {0, nullptr, nullptr};
+
+cudaError_t make_tensor_map_3d(CUtensorMap* tm, const void* base, const unsigned long long (&dims)[3],
+                               const unsigned long long (&strides_bytes)[2], const unsigned (&box)[3]) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;      // resolved once per process (idempotent, so a race only repeats the lookup)
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess) return e;
+    if (qres != cudaDriverEntryPointSuccess || !fn) return cudaErrorNotSupported;
+    encode = reinterpret_cast<EncodeFn>(fn);
+  }
+  const cuuint64_t gd[3] = {dims[0], dims[1], dims[2]}, gs[2] = {strides_bytes[0], strides_bytes[1]};
+  const cuuint32_t bx[3] = {box[0], box[1], box[2]}, es[3] = {1, 1, 1};
+  CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
 }
 
 namespace {

@@ -14,6 +14,8 @@
 //                    gradient of scales k >= 1; its extra grid rows do the deterministic pose reduction
 //                    (pose_final_block) and unpack the source-gradient texels into the planar grad_srcs
 //   k_pose_final     the same epilogue blocks on their own when S = 1
+#include <string.h>
+
 #include "colvo_kernels.cuh"
 
 // Ablation builds for the timing experiments logged under profiles/ (scripts/build_variants.py): they skip the
@@ -43,8 +45,11 @@
 #ifndef COLVO_BWD_SCATTER_MERGE
 #define COLVO_BWD_SCATTER_MERGE 0
 #endif
+#ifndef COLVO_BWD_TMA       // 1: the coefficient tile of a scale (34 x 6 windows x 3 channels of 16-byte texels) is ONE TMA
+#define COLVO_BWD_TMA 1     //    box load issued by one thread (UTMALDG; zero fill outside the image by the hardware);
+#endif                      //    0: 16-byte cp.async (LDGSTS) by every thread
 #ifndef COLVO_MINB_BWD      // CTAs per SM the register allocator must allow -- tuned on B200, see DESIGN.md
-#define COLVO_MINB_BWD (24 / COLVO_BWD_TILE_H)     // 24 warps per SM at 80 registers
+#define COLVO_MINB_BWD (20 / COLVO_BWD_TILE_H)     // 20 warps per SM at 96 registers (24 warps at 80 registers spill)
 #endif
 
 #ifdef COLVO_DEBUG_DUMP     // diagnostic builds only (tests/tools): per-pixel internals of k_photo_bwd at k = 0, source 0
@@ -59,6 +64,7 @@ namespace colvo {
 
 constexpr int kCH = kBwdTileH + 2, kCW = kTileW + 2;   // tile + 1-pixel halo (window centres)
 constexpr int kCN = kCH * kCW;
+constexpr int kCoefBuf = (kCN * 3 + 7) & ~7;           // float4 per coefficient buffer, padded to 128 bytes (TMA destination)
 
 // smoothness gradient of one depth texel from the saved adjoint field (grad_loss folded in by the caller)
 __device__ __forceinline__ float smooth_grad(float s, float D, float inv, float corr) {
@@ -66,7 +72,7 @@ __device__ __forceinline__ float smooth_grad(float s, float D, float inv, float 
   return -(s * inv - corr) * dr * dr;
 }
 
-// One CTA = one 32 x kBwdTileH (8) tile of one triplet.  The SSIM adjoint coefficients of every window were
+// One CTA = one 32 x kBwdTileH (4) tile of one triplet.  The SSIM adjoint coefficients of every window were
 // written by the forward (for the winning candidate; the winner flags ride in .w of channels 0 / 1), and
 // k_warp_stats saved the projection (u', v', iz, D^, valid) of every pixel, so the tile needs neither a halo
 // re-warp nor a re-projection: per scale the CTA stages the coefficient tile (+1 halo) in shared memory, every
@@ -93,18 +99,19 @@ __global__ void __launch_bounds__(kBwdThreads, COLVO_MINB_BWD)
                 const float* __restrict__ s_field0, const float* __restrict__ coef_in,
                 const float4* __restrict__ geo_in, float* __restrict__ grad_d0,
                 float* __restrict__ dD1, float* __restrict__ dD2, float* __restrict__ dD3,
-                float4* __restrict__ gsrc4, float* __restrict__ grad_src_depth, double* __restrict__ pose_part) {
+                float4* __restrict__ gsrc4, float* __restrict__ grad_src_depth, double* __restrict__ pose_part,
+                const __grid_constant__ CUtensorMap coef_map) {
   typedef Vn<NS> V;
   // dynamic shared memory, carved by hand
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float4 (*coef)[kCN * 3] = reinterpret_cast<float4 (*)[kCN * 3]>(smem_raw);   // [2]: (ca, cb, cg, flag) per window
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float4 (*coef)[kCoefBuf] = reinterpret_cast<float4 (*)[kCoefBuf]>(smem_raw);   // [2]: (ca, cb, cg, flag) per window
                                                                                // centre and channel, double-buffered over k
-  double* red = reinterpret_cast<double*>(smem_raw + sizeof(float4) * 2 * kCN * 3);
+  double* red = reinterpret_cast<double*>(smem_raw + sizeof(float4) * 2 * kCoefBuf);
   BwdConstV<NS>* cst = reinterpret_cast<BwdConstV<NS>*>(red + (kBwdThreads / 32) * NS * 12);    // [kMaxS]
   V* pose_s = reinterpret_cast<V*>(cst + kMaxS);                                            // [12]: R row-major, t; lane n
   float* cst_sm = reinterpret_cast<float*>(pose_s + 12);   // scale 0: 1/(mean+eps), sum(s d)/(n (mean+eps)^2)
   // full[i]: the copies into coefficient buffer i have landed (cp.async arrivals); empty[i]: every thread is done reading it
-  unsigned long long* mbar = reinterpret_cast<unsigned long long*>(smem_raw + sizeof(float4) * 2 * kCN * 3 +
+  unsigned long long* mbar = reinterpret_cast<unsigned long long*>(smem_raw + sizeof(float4) * 2 * kCoefBuf +
                                                                    sizeof(double) * (kBwdThreads / 32) * NS * 12 + 1024);
   static_assert(sizeof(BwdConstV<NS>) * kMaxS + sizeof(V) * 12 + 2 * sizeof(float) <= 1024, "constant area");
   // scatter exchange slots, [warp][lane][2]: lane l parks its two x1-column taps (value, texel offset) for lane l + 1
@@ -176,6 +183,14 @@ __global__ void __launch_bounds__(kBwdThreads, COLVO_MINB_BWD)
   // Coefficient tile of scale k (+1 halo; zeros outside the image), fetched with cp.async one scale ahead so its
   // global latency hides behind the previous scale's arithmetic.
   auto stage_coef = [&](int k) {
+#if COLVO_BWD_TMA
+    // one box load: [3 channels][kCH rows][kCW windows] of 16-byte texels, box origin (x0 - 1, y0 - 1); the part of the
+    // box outside the image arrives as zeros.  The bytes land on full[k & 1].
+    if (tid == 0) {
+      mbar_arrive_expect_tx(&mbar[k & 1], (unsigned)(sizeof(float4) * kCN * 3));
+      tma_load_3d(coef[k & 1], &coef_map, 4 * (x0 - 1), y0 - 1, (b * P.S + k) * 3, &mbar[k & 1]);
+    }
+#else
     float4* cbf = coef[k & 1];
     const float4* cin = reinterpret_cast<const float4*>(coef_in) + (long long)(b * P.S + k) * P.HW * 3;
     for (int idx = tid; idx < kCN; idx += kBwdThreads) {
@@ -184,17 +199,14 @@ __global__ void __launch_bounds__(kBwdThreads, COLVO_MINB_BWD)
       const bool on = gy >= 0 && gy < P.H && gx >= 0 && gx < P.W;
       const float4* p = on ? cin + (gy * P.W + gx) : cin;
 #pragma unroll
-      for (int ch = 0; ch < 3; ++ch) cp_async16(cbf + idx * 3 + ch, p + (long long)ch * P.HW, on);
+      for (int ch = 0; ch < 3; ++ch) cp_async16(cbf + ch * kCN + idx, p + (long long)ch * P.HW, on);
     }
     mbar_arrive_cp_async(&mbar[k & 1]);      // this thread's share of full[k & 1]
+#endif
   };
-  // active lanes of a warp are a prefix (one tile row: px grows with the lane); lane 0 has no left neighbour: its slot
-  // keeps a sentinel offset that matches no texel
-  const unsigned amask = __ballot_sync(0xffffffffu, in_img);
-  if (COLVO_BWD_SCATTER_MERGE && tx == 0) xch[0][0] = xch[0][1] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
   if (tid == 0) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) mbar_init(&mbar[i], kBwdThreads);
+    for (int i = 0; i < 4; ++i) mbar_init(&mbar[i], (COLVO_BWD_TMA && i < 2) ? 1 : kBwdThreads);   // full[0..1], empty[0..1]
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();       // barriers initialised; per-frame constants visible
@@ -229,7 +241,8 @@ __global__ void __launch_bounds__(kBwdThreads, COLVO_MINB_BWD)
     // once every thread has finished gathering from that buffer (scale k-1: a whole per-source phase ago), and the
     // gather of scale k starts once the copies into its buffer have landed -- warps drift by up to one scale.
     if (k + 1 < P.S) {
-      if (k >= 1) mbar_wait(&mbar[2 + ((k + 1) & 1)], ((k - 1) >> 1) & 1);     // empty[(k+1)&1]: gather(k-1) done everywhere
+      if (k >= 1 && (!COLVO_BWD_TMA || tid == 0))
+        mbar_wait(&mbar[2 + ((k + 1) & 1)], ((k - 1) >> 1) & 1);               // empty[(k+1)&1]: gather(k-1) done everywhere
       stage_coef(k + 1);
     }
     mbar_wait(&mbar[k & 1], (k >> 1) & 1);                                      // full[k&1]: scale k landed
@@ -245,7 +258,7 @@ __global__ void __launch_bounds__(kBwdThreads, COLVO_MINB_BWD)
       for (int j = 0; j < 9; ++j) {
         const int o = oc + (j / 3) * kCW + (j % 3);
         const float m = my3[j / 3] * mx3[j % 3];
-        const float4 q3[3] = {cb[o * 3], cb[o * 3 + 1], cb[o * 3 + 2]};
+        const float4 q3[3] = {cb[o], cb[kCN + o], cb[2 * kCN + o]};
         V mn;
         mn.set(0, m * q3[0].w);
         if (NS > 1) mn.set(NS - 1, m * q3[1].w);
@@ -266,7 +279,7 @@ __global__ void __launch_bounds__(kBwdThreads, COLVO_MINB_BWD)
       for (int j = 0; j < 9; ++j) {
         const int o = oc + (j / 3) * kCW + (j % 3);
         const float m = my3[j / 3] * mx3[j % 3];
-        const float4 q3[3] = {cb[o * 3], cb[o * 3 + 1], cb[o * 3 + 2]};
+        const float4 q3[3] = {cb[o], cb[kCN + o], cb[2 * kCN + o]};
         float mn[NS];
         mn[0] = m * q3[0].w;
         if (NS > 1) mn[NS - 1] = m * q3[1].w;
@@ -650,7 +663,7 @@ __global__ void __launch_bounds__(kThreads) k_zero(float4* __restrict__ a, long 
 
 template <int NS>
 static size_t photo_bwd_smem() {
-  return sizeof(float4) * 2 * kCN * 3 + sizeof(double) * (kBwdThreads / 32) * NS * 12 +
+  return sizeof(float4) * 2 * kCoefBuf + sizeof(double) * (kBwdThreads / 32) * NS * 12 +
          1024 /* per-frame constants, poses */ + 64 /* mbarriers */ +
          (COLVO_BWD_SCATTER_MERGE ? sizeof(float4) * 2 * kBwdThreads : 0) /* scatter exchange slots */;
 }
@@ -671,6 +684,16 @@ cudaError_t launch_backward(const KP& P, const BwdBuffers& Wk, const float* grad
     k_zero<<<148 * 4, kThreads, 0, st>>>(Wk.gsrc4, na, reinterpret_cast<float4*>(grad_src_depth), nb);
   }
   dim3 grid(P.tiles_x, P.btiles_y, P.B);
+  // the saved coefficient field [B,S,3,H,W] of 16-byte texels as a rank-3 fp32 tensor (4 W, H, 3 S B) for the TMA box loads
+  CUtensorMap coef_map;
+  memset(&coef_map, 0, sizeof(coef_map));
+  if (COLVO_BWD_TMA) {
+    const unsigned long long dims[3] = {4ull * P.W, (unsigned long long)P.H, 3ull * P.S * P.B};
+    const unsigned long long strides[2] = {16ull * P.W, 16ull * P.W * P.H};
+    const unsigned box[3] = {4u * kCW, (unsigned)kCH, 3u};
+    e = make_tensor_map_3d(&coef_map, sv.coef, dims, strides, box);
+    if (e != cudaSuccess) return e;
+  }
   {
     ScopedKernelTimer tm(2, st);
     // opting in to > 48 KB of dynamic shared memory is a per-function, per-device attribute: cheap and idempotent
@@ -679,11 +702,11 @@ cudaError_t launch_backward(const KP& P, const BwdBuffers& Wk, const float* grad
       if (zeroed)
         e = launch_pdl(kern, grid, dim3(kBwdThreads), smem, st, P, grad_loss, sel, (const double*)sv.frame, (const double*)sv.scale,
                        (const float*)sv.s_field[0], (const float*)sv.coef, (const float4*)sv.geo, grad_depth[0], Wk.dDhat[1],
-                       Wk.dDhat[2], Wk.dDhat[3], grad_srcs ? Wk.gsrc4 : nullptr, grad_src_depth, Wk.pose_part);
+                       Wk.dDhat[2], Wk.dDhat[3], grad_srcs ? Wk.gsrc4 : nullptr, grad_src_depth, Wk.pose_part, coef_map);
       else
         kern<<<grid, kBwdThreads, smem, st>>>(P, grad_loss, sel, sv.frame, sv.scale, sv.s_field[0], sv.coef, sv.geo, grad_depth[0],
                                            Wk.dDhat[1], Wk.dDhat[2], Wk.dDhat[3], grad_srcs ? Wk.gsrc4 : nullptr, grad_src_depth,
-                                           Wk.pose_part);
+                                           Wk.pose_part, coef_map);
     };
     const bool geo = P.src_depth != nullptr, pk = (P.flags & 16u) != 0;
     if (P.N == 1) {

@@ -1,5 +1,6 @@
 // Kernel parameter block, launch geometry and device helpers shared by the sm_100a kernels.
 #pragma once
+#include <cuda.h>            // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -13,9 +14,10 @@ constexpr int kMaxN = 2;
 constexpr int kThreads = 256;
 constexpr int kTileW = 32;       // one warp = one tile row: coalesced 128 B rows
 constexpr int kTileH = 8;
-// backward tile kernel (k_photo_bwd): 32 x kBwdTileH pixels, one thread each
+// backward tile kernel (k_photo_bwd): 32 x kBwdTileH pixels, one thread each.  32 x 4 tiles at 5 CTAs (20 warps, 96
+// registers) per SM with the coefficient tile fetched by TMA measured best on B200 (profiles/r2_bwd_tma_tiles.log)
 #ifndef COLVO_BWD_TILE_H
-#define COLVO_BWD_TILE_H 8
+#define COLVO_BWD_TILE_H 4
 #endif
 constexpr int kBwdTileH = COLVO_BWD_TILE_H;
 constexpr int kBwdThreads = 32 * kBwdTileH;
@@ -307,6 +309,21 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
       " @p bra D_%=;\n bra W_%=;\n"
       "D_%=:\n}\n" ::"r"(a), "r"(parity) : "memory");
 }
+
+// ---- TMA (cp.async.bulk.tensor): one elected thread moves a whole tile global -> shared; the bytes land on an mbarrier
+// (complete_tx), out-of-bounds elements of the box are zero-filled by the hardware ----
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, int c2, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n"
+               ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(tmap), "r"((unsigned)__cvta_generic_to_shared(bar)),
+                 "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+// host side: rank-3 fp32 tensor map, no swizzle, zero fill.  dims / box in elements (innermost first), strides in bytes
+// for dims 1 and 2.  Returns cudaSuccess or an error (no fallback: the caller reports it).
+cudaError_t make_tensor_map_3d(CUtensorMap* tm, const void* base, const unsigned long long (&dims)[3],
+                               const unsigned long long (&strides_bytes)[2], const unsigned (&box)[3]);
 
 // fire-and-forget float add to GLOBAL memory (RED.E.ADD.F32): explicit address space, so that a base pointer hidden
 // from the optimiser (see Img<false>::load_taps) does not turn into a generic atomic

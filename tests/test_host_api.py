@@ -43,6 +43,14 @@ def test_synthetic_generator_is_deterministic_and_shaped():
 
 def test_bench_algorithmic_bytes_match_survey():
     import bench
-    ab = bench.alg_bytes_per_triplet()
+    ab = bench.alg_bytes_per_triplet(256, 320)
     assert ab["step"] == 9_169_920 and ab["fwd"] == 3_384_320
     assert bench.alg_bytes_per_triplet(1080, 1350)["step"] == 163_202_040
+    assert bench.alg_bytes_per_pair(256, 320) == 2_293_760            # config 5
+    assert set(bench.CONFIGS) == {2, 4, 5} and bench.CONFIGS[2]["B"] == 12 and bench.CONFIGS[4]["W"] == 1350
+
+
+def test_source_hash_is_stable_and_sees_the_kernel_sources():
+    from coivo_b200 import _lib
+    h = _lib.source_hash()
+    assert len(h) == 16 and h == _lib.source_hash()
