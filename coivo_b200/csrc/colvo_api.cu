@@ -4,6 +4,9 @@
 #include <cuda_runtime.h>
 #include <string.h>
 
+#include <atomic>
+#include <mutex>
+
 #include "../../include/colvo.h"
 #include "colvo_kernels.cuh"
 
@@ -11,6 +14,29 @@ using namespace colvo;
 
 namespace colvo {
 KernelTimer g_timer = {0, nullptr, nullptr};
+
+cudaError_t ensure_dyn_smem(const void* kernel, size_t bytes) {
+  // (kernel, device) pairs already opted in; a handful of entries, appended under a lock, read lock-free
+  struct Entry { const void* fn; int dev; size_t bytes; };
+  static Entry table[64];
+  static std::atomic<int> count{0};
+  static std::mutex mu;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const int n = count.load(std::memory_order_acquire);
+  for (int i = 0; i < n; ++i)
+    if (table[i].fn == kernel && table[i].dev == dev && table[i].bytes >= bytes) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(mu);
+  const int m = count.load(std::memory_order_relaxed);
+  if (m < 64) {
+    table[m] = Entry{kernel, dev, bytes};
+    count.store(m + 1, std::memory_order_release);
+  }
+  return cudaSuccess;
+}
 
 cudaError_t make_tensor_map_3d(CUtensorMap* tm, const void* base, const unsigned long long (&dims)[3],
                                const unsigned long long (&strides_bytes)[2], const unsigned (&box)[3]) {

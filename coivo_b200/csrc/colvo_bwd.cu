@@ -696,9 +696,8 @@ cudaError_t launch_backward(const KP& P, const BwdBuffers& Wk, const float* grad
   }
   {
     ScopedKernelTimer tm(2, st);
-    // opting in to > 48 KB of dynamic shared memory is a per-function, per-device attribute: cheap and idempotent
     auto launch = [&](auto kern, size_t smem) {
-      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      ensure_dyn_smem(reinterpret_cast<const void*>(kern), smem);
       if (zeroed)
         e = launch_pdl(kern, grid, dim3(kBwdThreads), smem, st, P, grad_loss, sel, (const double*)sv.frame, (const double*)sv.scale,
                        (const float*)sv.s_field[0], (const float*)sv.coef, (const float4*)sv.geo, grad_depth[0], Wk.dDhat[1],

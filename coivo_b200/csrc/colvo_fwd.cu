@@ -642,7 +642,7 @@ cudaError_t launch_forward(const KP& P, const FwdBuffers& Wk, float* loss, float
     if (nb <= 0) return;
     dim3 g(div_up(P.W, kSmBW), div_up(P.H, kSmBH), nb);
     auto run = [&](auto kern) {
-      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_smem);
+      ensure_dyn_smem(reinterpret_cast<const void*>(kern), sm_smem);
       e = launch_pdl(kern, g, dim3(kThreads), sm_smem, st, P, smo, b0);
     };
     if (pk) run(k_smooth<true>); else run(k_smooth<false>);
@@ -654,9 +654,8 @@ cudaError_t launch_forward(const KP& P, const FwdBuffers& Wk, float* loss, float
   {
     ScopedKernelTimer tm(1, st);
     float4* co = save ? reinterpret_cast<float4*>(sv.coef) : nullptr;
-    // opting in to > 48 KB of dynamic shared memory is a per-function, per-device attribute: cheap and idempotent
     auto run = [&](auto kern, size_t smem) {
-      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      ensure_dyn_smem(reinterpret_cast<const void*>(kern), smem);
       e = launch_pdl(kern, grid, dim3(kFwdThreads), smem, st, P, ab, sel, Wk.loss_part, Wk.g_part, need_g, co, Wk.iw);
     };
     auto pick = [&](auto ns, auto pkc) {          // ADJ: the adjoint pieces are needed only when the forward saves for a backward

@@ -356,6 +356,10 @@ __device__ __forceinline__ void st_stream(T* p, const T& v) {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;\n" ::); }
 
+// Opting in to > 48 KB of dynamic shared memory is a per-function, per-device attribute: set once, then a table lookup
+// (no driver call on the launch path).  Implemented in colvo_api.cu.
+cudaError_t ensure_dyn_smem(const void* kernel, size_t bytes);
+
 // launch `kern` so that it may overlap the tail of the previous kernel in `st` (see pdl_wait)
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
