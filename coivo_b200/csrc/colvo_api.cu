@@ -309,10 +309,13 @@ int colvo_debug_time_kernel(int which, void* ev_start, void* ev_stop) {
 }
 
 // ---- consistency sweep ----------------------------------------------------------------------
-// pairs whose warped frames share one pass of the scratch buffer: at most 256 MB of texels
+// pairs whose warped frames share one pass of the scratch buffer: at most COLVO_SWEEP_PASS_MB of texels
+#ifndef COLVO_SWEEP_PASS_MB
+#define COLVO_SWEEP_PASS_MB 256
+#endif
 static int consistency_pairs_per_pass(int F, int H, int W) {
   const long long per = (long long)H * W * (long long)sizeof(float4);
-  long long n = (256ll << 20) / per;
+  long long n = ((long long)COLVO_SWEEP_PASS_MB << 20) / per;
   if (n < 1) n = 1;
   if (n > F - 1) n = F - 1;
   return (int)n;
