@@ -65,3 +65,54 @@ def test_world2_sharded_loss_equals_full_batch(B):
     full.backward()
     assert abs(glob - full.item()) < 1e-6
     assert torch.allclose(g, depth[0].grad, rtol=1e-4, atol=1e-9)
+
+
+def _ddp_worker(rank, world, port, B, q):
+    """sharded_loss(reduce="mean") under torch DDP: DDP AVERAGES the per-rank parameter gradients, so the local loss is
+    scaled by B_g * world / B.  The "network" is one learnable log-scale on a fixed depth pyramid."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    from coivo_b200.synthetic import make_triplets
+    from oracle import photometric as O
+    d = make_triplets(B, 24, 32, seed=6)
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.log_scale = torch.nn.Parameter(torch.zeros(()))
+
+        def forward(self, depth):
+            return [x * torch.exp(self.log_scale) for x in depth]
+
+    net = torch.nn.parallel.DistributedDataParallel(Net())
+    batch = dict(d)
+    batch["depth"] = net(d["depth"])
+    scaled, glob = cdist.sharded_loss(O.photometric_loss, batch, reduce="mean")
+    scaled.backward()                       # DDP all-reduces and divides by world
+    if rank == 0:
+        q.put((glob.item(), net.module.log_scale.grad.item()))
+    dist.destroy_process_group()
+
+
+def test_world2_sharded_loss_mean_under_ddp_matches_the_global_gradient():
+    B = 3                                   # uneven shards: 2 + 1
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, B, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    glob, g = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    from coivo_b200.synthetic import make_triplets
+    from oracle import photometric as O
+    d = make_triplets(B, 24, 32, seed=6)
+    ls = torch.zeros((), requires_grad=True)
+    full = O.photometric_loss([x * torch.exp(ls) for x in d["depth"]], d["pose"], d["K"], d["tgt"], d["srcs"])
+    full.backward()
+    assert abs(glob - full.item()) < 1e-6
+    assert abs(g - ls.grad.item()) <= 1e-4 * abs(ls.grad.item()) + 1e-9

@@ -344,6 +344,20 @@ def test_geometric_consistency_term_parity(B, H, W, N, S):
     assert relinf(sdg.grad, osd.grad) < TOL
 
 
+def test_geometric_term_switched_off_gives_no_source_depth_gradient():
+    """with `geo_weight == 0` (the default, or the start of a weight ramp) the source depth maps take no part:
+    their gradient is None -- not an uninitialised buffer -- and the loss equals the plain one."""
+    d = make_triplets(2, 32, 48, seed=44)
+    sd = (1.0 + 0.5 * torch.rand(2, 2, 1, 32, 48)).to(DEV).requires_grad_()
+    depth = [x.to(DEV).requires_grad_() for x in d["depth"]]
+    args = (d["pose"].to(DEV), d["K"].to(DEV), d["tgt"].to(DEV), d["srcs"].to(DEV))
+    loss = coivo_b200.photometric_loss(depth, *args, src_depth=sd, geo_weight=0.0)
+    loss.backward()
+    assert sd.grad is None and depth[0].grad is not None and torch.isfinite(depth[0].grad).all()
+    with torch.no_grad():
+        assert loss.item() == coivo_b200.photometric_loss([x.detach() for x in depth], *args).item()
+
+
 @pytest.mark.parametrize("B,H,W,N,S", [(2, 48, 64, 2, 4), (1, 37, 53, 1, 3)])
 def test_packed_bf16_image_storage_parity(B, H, W, N, S):
     """images stored as RGBA bf16 (8 B/pixel), fp32 arithmetic.  The oracle runs on
