@@ -408,36 +408,44 @@ __global__ void __launch_bounds__(kThreads)
     }
     __syncthreads();
     double acc[2] = {0.0, 0.0};                       // photometric sum, weighted smoothness (+ geometric) sum
-    for (int i = threadIdx.x; i < P.B * tiles; i += kThreads) acc[0] += loss_part[i];
+    {
+      // four independent partial sums per thread: the loads of four strides are in flight together (this block is
+      // latency-bound: 15 k partials at 1080x1350); fixed order, so the result is reproducible
+      const int n = P.B * tiles;
+      double a4[4] = {0.0, 0.0, 0.0, 0.0};
+      int i = threadIdx.x;
+      for (; i + 3 * kThreads < n; i += 4 * kThreads) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) a4[u] += loss_part[i + u * kThreads];
+      }
+      for (; i < n; i += kThreads) a4[0] += loss_part[i];
+      acc[0] = (a4[0] + a4[1]) + (a4[2] + a4[3]);
+    }
     if (P.src_depth) {                                // L_geo,k = sum of diffs / (B N HW), weight geo_weight
       const double wg = (double)P.geo_weight / ((double)P.B * (double)P.N * (double)P.HW);
       for (int i = threadIdx.x; i < BNS * stat_chunks; i += kThreads) acc[1] += stat_part[(long long)i * kStatVals + 5] * wg;
     }
-    // smoothness: four lanes per (b, k) sum the partials of that image's k_smooth CTAs (64 pairs per pass of the
-    // block, fixed order), then 1 / (mean d + eps) is applied (see k_smooth)
+    // smoothness: one warp per (b, k) sums the partials of that image's k_smooth CTAs (8 pairs per pass of the block,
+    // fixed order), then 1 / (mean d + eps) is applied (see k_smooth)
     {
-      const int grp = threadIdx.x >> 2, sub = threadIdx.x & 3;
-      for (int bk0 = 0; bk0 < P.B * P.S; bk0 += kThreads / 4) {
-        const int bk = bk0 + grp;
+      for (int bk0 = 0; bk0 < P.B * P.S; bk0 += kThreads / 32) {
+        const int bk = bk0 + wid;
         const bool on = bk < P.B * P.S;
         const int b = on ? bk / P.S : 0, k = on ? bk - b * P.S : 0;
         const double* sp = smooth_part + ((long long)b * P.sm_blocks * P.S + k) * kSmVals;
         double sx = 0.0, sy = 0.0, sd = 0.0;
         if (on) {
-          for (int t = sub; t < P.sm_blocks; t += 4) {
+          for (int t = lane; t < P.sm_blocks; t += 32) {
             const double* q = sp + (long long)t * P.S * kSmVals;
             sx += q[0];
             sy += q[1];
             sd += q[3];
           }
         }
-#pragma unroll
-        for (int o = 1; o < 4; o <<= 1) {
-          sx += __shfl_xor_sync(0xffffffffu, sx, o);
-          sy += __shfl_xor_sync(0xffffffffu, sy, o);
-          sd += __shfl_xor_sync(0xffffffffu, sd, o);
-        }
-        if (on && sub == 0) {
+        sx = warp_sum(sx);
+        sy = warp_sum(sy);
+        sd = warp_sum(sd);
+        if (on && lane == 0) {
           const double mean = sd / ((double)P.h[k] * (double)P.w[k]);
           acc[1] += (sx * wk_s[k][0] + sy * wk_s[k][1]) / (mean + (double)P.eps_disp);
         }
