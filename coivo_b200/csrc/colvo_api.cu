@@ -125,7 +125,7 @@ void fill_params(KP& P, const ColvoDesc* d) {
 
 size_t smooth_tiles(const ColvoDesc* d) { return (size_t)div_up(d->W, kSmBW) * div_up(d->H, kSmBH) * d->S; }
 
-int stat_chunks(const ColvoDesc* d) { return div_up(d->H * d->W, kThreads * kStatPPT); }
+int stat_chunks(const ColvoDesc* d) { return div_up(d->H * d->W, stats_pixels_per_cta(d->S)); }
 
 size_t carve_fwd(const ColvoDesc* d, void* ws, FwdBuffers& F) {
   Carver c(ws);

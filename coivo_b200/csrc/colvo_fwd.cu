@@ -198,17 +198,28 @@ __global__ void __launch_bounds__(kThreads)
 //   N = 1:  iw[(b,k)][pix] = (x0, x1, x2, valid)                                   16 B / pixel
 //   N = 2:  iwA[(b,k)][pix] = (x0^0, x0^1, x1^0, x1^1), iwB[(b,k)][pix] = (x2^0, x2^1)   24 B / pixel for both sources
 // (iwB starts B*S*HW float4 behind iw), i.e. channel c of both sources is one aligned register pair downstream.
-template <int NS, bool GEO, bool PK>
-__global__ void __launch_bounds__(kThreads, COLVO_MINB_STATS)
+//
+// KIN (training loss, S > 1): one CTA = one chunk of pixels of one triplet for ALL scales, scale after scale -- the four
+// scales gather from the same source lines, so scales 1.. find them in L1 (with one CTA per (b, k) they sat in the L1s of
+// different SMs); 128-thread CTAs of kStatPPTK pixels per thread and scale keep the CTA count (and the pixels in flight per
+// thread) of the one-scale form.  !KIN (consistency sweep, S = 1): blockIdx.y = (b, k), 256 threads, kStatPPT pixels each.
+template <bool KIN> struct StatCfg { static constexpr int NT = KIN ? kStatThreadsK : kThreads, PPT = KIN ? kStatPPTK : kStatPPT; };
+template <int NS, bool GEO, bool PK, bool KIN>
+__global__ void __launch_bounds__(StatCfg<KIN>::NT, COLVO_MINB_STATS * kThreads / StatCfg<KIN>::NT)
     k_warp_stats(KP P, double* __restrict__ part, uint8_t* __restrict__ valid_out, float4* __restrict__ iw_out,
                  float4* __restrict__ geo_out, float* __restrict__ occ_out) {
   constexpr int NA = GEO ? kStatVals : 5;      // accumulators per source (the 6th only with the geometric term)
   constexpr int NV = NA * NS;
+  constexpr int NT = StatCfg<KIN>::NT, PPT = StatCfg<KIN>::PPT;
   typedef Vn<NS> V;
-  __shared__ double sm[(kThreads / 32) * NV];
+  __shared__ double sm[(NT / 32) * NV];
   pdl_trigger();                               // k_lcc_solve / k_photo_fwd may start their prologues in this kernel's tail
-  const int bk = blockIdx.y, k = bk % P.S, b = bk / P.S;
-  const Cam cam = load_cam(P, b);
+  const int b = KIN ? (int)blockIdx.y : (int)blockIdx.y / P.S;
+  const int k_lo = KIN ? 0 : (int)blockIdx.y % P.S, k_hi = KIN ? P.S : k_lo + 1;
+#pragma unroll 1
+  for (int k = k_lo; k < k_hi; ++k) {
+  const Cam cam = load_cam(P, b);               // (re-loaded per scale: cheaper than 28 registers held across the loop)
+  const PoseV<NS> pose = load_pose_v<NS>(P, b);
   const float* Dk = P.depth[k] + (long long)b * P.depth_bs[k];
   Img<PK> tg = img_at<PK>(P, P.tgt, b * P.tgt_bf);
   // Loop-invariant bases, materialised once and hidden from the optimiser (which otherwise re-derives the 64-bit
@@ -228,15 +239,14 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_STATS)
   float2* iw_b2 = (iw_out && NS == 2) ? reinterpret_cast<float2*>(iw_out + (long long)P.B * P.S * P.HW) + (long long)(b * P.S + k) * P.HW
                                       : nullptr;
   asm volatile("" : "+l"(tg.p), "+l"(src0.p), "+l"(valid_b), "+l"(iw_a), "+l"(iw_b2), "+l"(geo_b), "+l"(geo_b2));
-  const PoseV<NS> pose = load_pose_v<NS>(P, b);
-  int pix = blockIdx.x * (kThreads * kStatPPT) + threadIdx.x;
+  int pix = blockIdx.x * (NT * PPT) + threadIdx.x;
   int py = pix / P.W, px = pix - py * P.W;
   double acc[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) acc[i] = 0.0;
-  constexpr int kUnroll = COLVO_STATS_UNROLL;
+  constexpr int kUnroll = COLVO_STATS_UNROLL < PPT ? COLVO_STATS_UNROLL : PPT;
 #pragma unroll kUnroll
-  for (int i = 0; i < kStatPPT; ++i) {
+  for (int i = 0; i < PPT; ++i) {
     if (pix < P.HW) {
       const float rx = ray_x(px, cam), ry = ray_y(py, cam);
       const float D = depth_at(P, Dk, k, px, py);
@@ -321,8 +331,8 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_STATS)
         if (GEO && occ_b) occ_b[opix] = occ;
       }
     }
-    pix += kThreads;
-    px += kThreads;
+    pix += NT;
+    px += NT;
     while (px >= P.W) { px -= P.W; ++py; }
   }
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -335,10 +345,12 @@ __global__ void __launch_bounds__(kThreads, COLVO_MINB_STATS)
   if (threadIdx.x < NV) {
     double s = 0.0;
 #pragma unroll
-    for (int w = 0; w < kThreads / 32; ++w) s += sm[w * NV + threadIdx.x];
+    for (int w = 0; w < NT / 32; ++w) s += sm[w * NV + threadIdx.x];
     const int n = threadIdx.x / NA, j = threadIdx.x - NA * n;
     const int bnk = (b * P.N + n) * P.S + k;
     part[((long long)bnk * gridDim.x + blockIdx.x) * kStatVals + j] = s;
+  }
+  if (KIN) __syncthreads();      // sm is reused by the next scale
   }
 }
 
@@ -626,15 +638,24 @@ cudaError_t launch_forward(const KP& P, const FwdBuffers& Wk, float* loss, float
   const bool pk = (P.flags & 16u) != 0;
   {
     ScopedKernelTimer tm(3, st);
-    dim3 g(Wk.stat_chunks, P.B * P.S);
     const bool geo = P.src_depth != nullptr;
-    auto run = [&](auto kern) { kern<<<g, kThreads, 0, st>>>(P, Wk.stat_part, valid, Wk.iw, save ? sv.geo : nullptr, occ); };
+    const bool kin = stats_k_inner(P.S);
+    dim3 g(Wk.stat_chunks, kin ? P.B : P.B * P.S);
+    const int nt = kin ? kStatThreadsK : kThreads;
+    auto run = [&](auto kern) { kern<<<g, nt, 0, st>>>(P, Wk.stat_part, valid, Wk.iw, save ? sv.geo : nullptr, occ); };
+    auto pick = [&](auto ns, auto geoc, auto pkc) {
+      constexpr int NSc = decltype(ns)::value;
+      constexpr bool Gc = decltype(geoc)::value, PKc = decltype(pkc)::value;
+      if (kin) run(k_warp_stats<NSc, Gc, PKc, true>); else run(k_warp_stats<NSc, Gc, PKc, false>);
+    };
+    using I1 = std::integral_constant<int, 1>; using I2 = std::integral_constant<int, 2>;
+    using T = std::true_type; using F = std::false_type;
     if (P.N == 1) {
-      if (geo) { if (pk) run(k_warp_stats<1, true, true>); else run(k_warp_stats<1, true, false>); }
-      else { if (pk) run(k_warp_stats<1, false, true>); else run(k_warp_stats<1, false, false>); }
+      if (geo) { if (pk) pick(I1{}, T{}, T{}); else pick(I1{}, T{}, F{}); }
+      else { if (pk) pick(I1{}, F{}, T{}); else pick(I1{}, F{}, F{}); }
     } else {
-      if (geo) { if (pk) run(k_warp_stats<2, true, true>); else run(k_warp_stats<2, true, false>); }
-      else { if (pk) run(k_warp_stats<2, false, true>); else run(k_warp_stats<2, false, false>); }
+      if (geo) { if (pk) pick(I2{}, T{}, T{}); else pick(I2{}, T{}, F{}); }
+      else { if (pk) pick(I2{}, F{}, T{}); else pick(I2{}, F{}, F{}); }
     }
   }
   cudaError_t e = launch_pdl(k_lcc_solve, dim3(BNS), dim3(32), 0, st, P, Wk.stat_part, Wk.stat_chunks, ab,
@@ -703,7 +724,7 @@ cudaError_t launch_consistency(const KP& P0, double* stat_part, int stat_chunks,
     float* abp = ab + 2 * p0;
     {
       ScopedKernelTimer tm(3, st);
-      k_warp_stats<1, false, false><<<dim3(stat_chunks, P.B), kThreads, 0, st>>>(P, sp, nullptr, iw, nullptr, nullptr);
+      k_warp_stats<1, false, false, false><<<dim3(stat_chunks, P.B), kThreads, 0, st>>>(P, sp, nullptr, iw, nullptr, nullptr);
     }
     k_lcc_solve<<<P.B, 32, 0, st>>>(P, sp, stat_chunks, abp, nullptr);
     {

@@ -32,7 +32,14 @@ constexpr int kFwdTileH = kFwdWarps * kFwdRows;   // 12
 #ifndef COLVO_STAT_PPT
 #define COLVO_STAT_PPT 8
 #endif
-constexpr int kStatPPT = COLVO_STAT_PPT;   // pixels per thread in the LCC statistics pass
+constexpr int kStatPPT = COLVO_STAT_PPT;   // pixels per thread in the LCC statistics pass (one scale per CTA: the sweep)
+// training loss (S > 1): one CTA walks all scales of its pixel chunk (see k_warp_stats), 128 threads x 4 pixels per scale
+#ifndef COLVO_STATS_KINNER
+#define COLVO_STATS_KINNER 1
+#endif
+constexpr int kStatThreadsK = 128, kStatPPTK = 4;
+inline bool stats_k_inner(int S) { return COLVO_STATS_KINNER && S > 1; }
+inline int stats_pixels_per_cta(int S) { return stats_k_inner(S) ? kStatThreadsK * kStatPPTK : kThreads * kStatPPT; }
 constexpr int kStatVals = 6;     // per (frame, chunk): n, Sx, Sy, Sxx, Sxy, sum of geometric-consistency diffs
 #ifndef COLVO_SM_BW
 #define COLVO_SM_BW 64
