@@ -2,6 +2,8 @@
 // workspace carving and kernel launches on the caller's stream.  No allocation, no
 // synchronisation, no retained state; there is no CPU fallback.
 #include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -54,9 +56,22 @@ cudaError_t make_tensor_map_3d(CUtensorMap* tm, const void* base, const unsigned
   }
   const cuuint64_t gd[3] = {dims[0], dims[1], dims[2]}, gs[2] = {strides_bytes[0], strides_bytes[1]};
   const cuuint32_t bx[3] = {box[0], box[1], box[2]}, es[3] = {1, 1, 1};
-  CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+  auto call = [&]() {
+    return encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  };
+  CUresult r = call();
+  if (r == CUDA_ERROR_INVALID_CONTEXT || r == CUDA_ERROR_NOT_INITIALIZED) {
+    // The encoder is a DRIVER entry point: it needs the device's primary context current on the calling thread, which the
+    // runtime only guarantees after its first call there -- autograd runs the backward on its own thread, and with
+    // COLVO_F_NO_SRC_GRAD this is the first CUDA call of that thread.  Bind the context through the runtime and retry.
+    cudaFree(nullptr);
+    r = call();
+  }
+  if (r != CUDA_SUCCESS && getenv("COLVO_DEBUG"))      // diagnostics on request only: the library itself never prints
+    fprintf(stderr, "colvo: cuTensorMapEncodeTiled -> %d  base %p dims %llu %llu %llu strides %llu %llu box %u %u %u\n", (int)r, base,
+            dims[0], dims[1], dims[2], strides_bytes[0], strides_bytes[1], box[0], box[1], box[2]);
+  return r == CUDA_SUCCESS ? cudaSuccess : static_cast<cudaError_t>(COLVO_E_TENSOR_MAP);
 }
 }
 
@@ -203,6 +218,7 @@ const char* colvo_error_string(int rc) {
     case COLVO_E_NULL_PTR: return "colvo: required pointer is NULL";
     case COLVO_E_MISALIGNED: return "colvo: pointer not aligned (fp32 buffers 4 B, saved 8 B, workspace 256 B)";
     case COLVO_E_UNSUPPORTED: return "colvo: unsupported configuration (e.g. grad_srcs with packed bf16 images)";
+    case COLVO_E_TENSOR_MAP: return "colvo: the driver refused a TMA tensor map (cuTensorMapEncodeTiled)";
     default: break;
   }
   if (rc > 0) return cudaGetErrorString(static_cast<cudaError_t>(rc));

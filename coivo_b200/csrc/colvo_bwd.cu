@@ -250,6 +250,7 @@ __global__ void __launch_bounds__(kBwdThreads, COLVO_MINB_BWD)
     // one pass over the 3x3 neighbourhood serves all sources with exact zeros for the others (the three sums cancel
     // heavily against each other downstream)
     V A[3], Bc[3], G[3];
+    CV_CHECK(oc >= 0 && oc + 2 * kCW + 2 < kCN && 3 * kCN <= kCoefBuf);
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) A[ch] = Bc[ch] = G[ch] = bc<NS>(0.f);
     if (in_img && !COLVO_EXP_NOGATHER) {
@@ -320,6 +321,7 @@ __global__ void __launch_bounds__(kBwdThreads, COLVO_MINB_BWD)
         for (int i = 0; i < M; ++i) {
           const Img<PK> src = img_at<PK>(P, P.srcs, b * P.src_bf + (n0 + i) * P.src_nf);
           t[i] = make_taps(gu_.lane(i), gv_.lane(i), P.W, P.H);
+          CV_CHECK_TAPS(t[i], P.W, P.H);
           r0[i] = t[i].y0 * P.W;
           r1[i] = t[i].y1 * P.W;
           src.load_taps(r0[i] + t[i].x0, r0[i] + t[i].x1, r1[i] + t[i].x0, r1[i] + t[i].x1, tx4[i]);
@@ -378,6 +380,7 @@ __global__ void __launch_bounds__(kBwdThreads, COLVO_MINB_BWD)
             const float a00 = w00.lane(i), a01 = w01.lane(i), a10 = w10.lane(i), a11 = w11.lane(i);
             const float h0 = hq[0].lane(i), h1 = hq[1].lane(i), h2 = hq[2].lane(i);
             const int o00 = r0[i] + t[i].x0, o01 = r0[i] + t[i].x1, o10 = r1[i] + t[i].x0, o11 = r1[i] + t[i].x1;
+            CV_CHECK(o00 >= 0 && o11 < P.HW && o01 < P.HW && o10 < P.HW);
 #if COLVO_BWD_SCATTER_MERGE
             // Warp-aggregated scatter (north_star: no contended global atomics).  Neighbouring pixels of a row sample
             // neighbouring texels, so the right-hand taps (x1, y0), (x1, y1) of lane l usually ARE the left-hand taps
@@ -596,7 +599,10 @@ __global__ void __launch_bounds__(kThreads)
           const float* rowp = dD + v * P.W;
           float row = 0.f;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) row = fmaf(wx[c], __ldg(rowp + imin(imax(ub + c, 0), P.W - 1)), row);
+          for (int c = 0; c < 4; ++c) {
+            CV_CHECK(v * P.W + imin(imax(ub + c, 0), P.W - 1) < P.HW);
+            row = fmaf(wx[c], __ldg(rowp + imin(imax(ub + c, 0), P.W - 1)), row);
+          }
           acc = fmaf(w, row, acc);
         }
       }
@@ -631,7 +637,10 @@ __global__ void __launch_bounds__(kThreads)
         float row = 0.f;
 #pragma unroll
         for (int c = 0; c < 8; ++c)
-          if (wxs[c] != 0.f) row = fmaf(wxs[c], __ldg(rowp + c * G), row);
+          if (wxs[c] != 0.f) {
+            CV_CHECK(v >= 0 && v < P.H && ub + c * G >= 0 && ub + c * G < P.W);
+            row = fmaf(wxs[c], __ldg(rowp + c * G), row);
+          }
         acc = fmaf(wy, row, acc);
       }
     }
@@ -697,7 +706,8 @@ cudaError_t launch_backward(const KP& P, const BwdBuffers& Wk, const float* grad
   {
     ScopedKernelTimer tm(2, st);
     auto launch = [&](auto kern, size_t smem) {
-      ensure_dyn_smem(reinterpret_cast<const void*>(kern), smem);
+      e = ensure_dyn_smem(reinterpret_cast<const void*>(kern), smem);
+      if (e != cudaSuccess) return;
       if (zeroed)
         e = launch_pdl(kern, grid, dim3(kBwdThreads), smem, st, P, grad_loss, sel, (const double*)sv.frame, (const double*)sv.scale,
                        (const float*)sv.s_field[0], (const float*)sv.coef, (const float4*)sv.geo, grad_depth[0], Wk.dDhat[1],
@@ -706,6 +716,7 @@ cudaError_t launch_backward(const KP& P, const BwdBuffers& Wk, const float* grad
         kern<<<grid, kBwdThreads, smem, st>>>(P, grad_loss, sel, sv.frame, sv.scale, sv.s_field[0], sv.coef, sv.geo, grad_depth[0],
                                            Wk.dDhat[1], Wk.dDhat[2], Wk.dDhat[3], grad_srcs ? Wk.gsrc4 : nullptr, grad_src_depth,
                                            Wk.pose_part, coef_map);
+      if (e == cudaSuccess) e = cudaGetLastError();
     };
     const bool geo = P.src_depth != nullptr, pk = (P.flags & 16u) != 0;
     if (P.N == 1) {
@@ -716,6 +727,7 @@ cudaError_t launch_backward(const KP& P, const BwdBuffers& Wk, const float* grad
       else { if (pk) launch(k_photo_bwd<2, false, true>, photo_bwd_smem<2>()); else launch(k_photo_bwd<2, false, false>, photo_bwd_smem<2>()); }
     }
   }
+  if (e != cudaSuccess) return e;
   // epilogue: pose reduction, source-gradient unpack and the up-sample adjoint are independent of each other, so they
   // share one launch (programmatic, so its CTAs are resident by the time k_photo_bwd drains)
   PoseFinalArgs A;

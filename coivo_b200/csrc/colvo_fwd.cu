@@ -248,6 +248,7 @@ __global__ void __launch_bounds__(StatCfg<KIN>::NT, COLVO_MINB_STATS * kThreads 
 #pragma unroll kUnroll
   for (int i = 0; i < PPT; ++i) {
     if (pix < P.HW) {
+      CV_CHECK(py < P.H && px < P.W && py * P.W + px == pix);
       const float rx = ray_x(px, cam), ry = ray_y(py, cam);
       const float D = depth_at(P, Dk, k, px, py);
       float y0, y1, y2;
@@ -265,6 +266,7 @@ __global__ void __launch_bounds__(StatCfg<KIN>::NT, COLVO_MINB_STATS * kThreads 
 #pragma unroll
       for (int n = 0; n < NS; ++n) {
         t[n] = make_taps(g.u.lane(n), g.v.lane(n), P.W, P.H);
+        CV_CHECK_TAPS(t[n], P.W, P.H);
         const int foff = n * src_noff;
         const int r0 = foff + t[n].y0 * P.W, r1 = foff + t[n].y1 * P.W;
         src0.load_taps(r0 + t[n].x0, r0 + t[n].x1, r1 + t[n].x0, r1 + t[n].x1, tx[n]);
@@ -671,7 +673,8 @@ cudaError_t launch_forward(const KP& P, const FwdBuffers& Wk, float* loss, float
     if (nb <= 0) return;
     dim3 g(div_up(P.W, kSmBW), div_up(P.H, kSmBH), nb);
     auto run = [&](auto kern) {
-      ensure_dyn_smem(reinterpret_cast<const void*>(kern), sm_smem);
+      e = ensure_dyn_smem(reinterpret_cast<const void*>(kern), sm_smem);
+      if (e != cudaSuccess) return;
       e = launch_pdl(kern, g, dim3(kThreads), sm_smem, st, P, smo, b0);
     };
     if (pk) run(k_smooth<true>); else run(k_smooth<false>);
@@ -684,7 +687,8 @@ cudaError_t launch_forward(const KP& P, const FwdBuffers& Wk, float* loss, float
     ScopedKernelTimer tm(1, st);
     float4* co = save ? reinterpret_cast<float4*>(sv.coef) : nullptr;
     auto run = [&](auto kern, size_t smem) {
-      ensure_dyn_smem(reinterpret_cast<const void*>(kern), smem);
+      e = ensure_dyn_smem(reinterpret_cast<const void*>(kern), smem);
+      if (e != cudaSuccess) return;
       e = launch_pdl(kern, grid, dim3(kFwdThreads), smem, st, P, ab, sel, Wk.loss_part, Wk.g_part, need_g, co, Wk.iw);
     };
     auto pick = [&](auto ns, auto pkc) {          // ADJ: the adjoint pieces are needed only when the forward saves for a backward

@@ -7,6 +7,25 @@
 #include "colvo_math.cuh"
 #include "colvo_f2.cuh"
 
+// Debug build with index checks (-DCOLVO_DEBUG_BOUNDS=1; scripts/build_variants.py bounds=COLVO_DEBUG_BOUNDS=1): every
+// computed gather / scatter / shared-memory index is asserted before use and a violation traps the kernel with a message.
+// compute-sanitizer is closed on the GPU pool these kernels are developed on; the GPU parity tests are run once per
+// kernel change against this build instead (COLVO_LIB=build/variants/lib_bounds.so pytest -m gpu).
+#if defined(COLVO_DEBUG_BOUNDS) && COLVO_DEBUG_BOUNDS
+#include <stdio.h>
+#define CV_CHECK(cond)                                                                                              \
+  do {                                                                                                              \
+    if (!(cond)) {                                                                                                  \
+      printf("colvo bounds check failed: %s  (%s:%d, block %d,%d,%d thread %d)\n", #cond, __FILE__, __LINE__,        \
+             (int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z, (int)threadIdx.x);                                  \
+      __trap();                                                                                                     \
+    }                                                                                                               \
+  } while (0)
+#else
+#define CV_CHECK(cond) ((void)0)
+#endif
+#define CV_CHECK_TAPS(t, W, H) CV_CHECK((t).x0 >= 0 && (t).x0 <= (t).x1 && (t).x1 < (W) && (t).y0 >= 0 && (t).y0 <= (t).y1 && (t).y1 < (H))
+
 namespace colvo {
 
 constexpr int kMaxS = 4;
@@ -156,6 +175,7 @@ __device__ __forceinline__ float depth_at(const KP& P, const float* __restrict__
   const int wk = P.w[k];
   Axis ay = upsample_axis(py, P.ry[k], P.h[k]);
   Axis ax = upsample_axis(px, P.rx[k], wk);
+  CV_CHECK(ay.i0 >= 0 && ay.i1 < P.h[k] && ax.i0 >= 0 && ax.i1 < wk);
   float d00 = __ldg(Dk + ay.i0 * wk + ax.i0);
   float d01 = __ldg(Dk + ay.i0 * wk + ax.i1);
   float d10 = __ldg(Dk + ay.i1 * wk + ax.i0);

@@ -121,6 +121,7 @@ __global__ void __launch_bounds__(kFwdThreads, COLVO_MINB_FWD)
     const int idx = tid + j * kFwdThreads;
     const int r = idx / kDW, c = idx - r * kDW;
     goff[j] = (idx < kDN) ? reflect_clamp(y0 - 1 + r, P.H) * P.W + reflect_clamp(x0 - 1 + c, P.W) : -1;
+    CV_CHECK(goff[j] < P.HW);
   }
   auto stage_scale = [&](int k, int buf) {      // warped frames of scale k -> sm.xa / sm.xb [buf]
     // frame base hidden from the optimiser + 32-bit offsets: one IMAD.WIDE per copy (see Img<false>::load_taps);
@@ -291,6 +292,7 @@ __global__ void __launch_bounds__(kFwdThreads, COLVO_MINB_FWD)
 #pragma unroll
       for (int j = 0; j < kFwdRows + 2; ++j) {
         const int o = (trow0 + j) * kDW + lane;
+        CV_CHECK(o + 2 < kDN);
         row_sums<NS, false>(R[j % 3], Y[j % 3], sm.y, sm.xa[buf], sm.xb[buf], o);
         if (j >= 2) {
           const int wr = trow0 + j - 2, py = y0 + wr;

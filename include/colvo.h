@@ -52,6 +52,7 @@ extern "C" {
 #define COLVO_E_NULL_PTR (-3)
 #define COLVO_E_MISALIGNED (-4)
 #define COLVO_E_UNSUPPORTED (-5)
+#define COLVO_E_TENSOR_MAP (-6)    /* cuTensorMapEncodeTiled refused the TMA descriptor of an internal buffer */
 
 /* Problem descriptor.  h[k] = H >> k, w[k] = W >> k must hold (oracle A1/A3). */
 typedef struct ColvoDesc {

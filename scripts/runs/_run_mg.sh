@@ -1,4 +1,4 @@
-# usage: bash scripts/_run_mg.sh N   -- weak + strong scaling lines at N GPUs (and the NCCL sharded_loss test at N = 2)
+# usage: bash scripts/runs/_run_mg.sh N   -- weak + strong scaling lines at N GPUs (and the NCCL sharded_loss test at N = 2)
 N=$1
 mkdir -p gpurun_out/r2
 nvidia-smi topo -m > gpurun_out/r2/topo_$N.txt 2>&1

@@ -419,3 +419,30 @@ def test_concurrent_streams_are_reentrant():
                 assert torch.equal(depth[k].grad.cpu(), ref[i][4][k])       # deterministic outputs: bit-equal
             assert torch.equal(pose.grad.cpu(), ref[i][5])
             assert relinf(srcs.grad, ref[i][6]) < 1e-5                      # float atomics
+
+
+def test_backward_as_first_cuda_call_of_a_fresh_thread():
+    """The backward builds a TMA descriptor through a driver entry point, which needs the primary context current on the
+    calling thread.  A fresh host thread whose FIRST CUDA call is that backward (no source gradient: no zero-fill launch
+    in front of it) must work -- this is what autograd's own thread looks like in a new process."""
+    import ctypes
+    import threading
+    from coivo_b200 import _lib
+    d = make_triplets(2, 24, 40, seed=51)
+    depth = [x.to(DEV).requires_grad_() for x in d["depth"]]
+    pose = d["pose"].to(DEV).requires_grad_()
+    tp, sp = coivo_b200.pack_images(d["tgt"]).to(DEV), coivo_b200.pack_images(d["srcs"]).to(DEV)
+    loss = coivo_b200.photometric_loss(depth, pose, d["K"].to(DEV), tp, sp)
+    out = {}
+
+    def worker():
+        try:
+            loss.backward()
+            torch.cuda.synchronize()
+            out["ok"] = True
+        except Exception as e:          # noqa: BLE001
+            out["err"] = str(e)
+    t = threading.Thread(target=worker)
+    t.start(); t.join()
+    assert out.get("ok"), out.get("err")
+    assert torch.isfinite(depth[0].grad).all() and torch.isfinite(pose.grad).all()
