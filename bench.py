@@ -369,6 +369,21 @@ def run_loss(args, cfg, cfg_id):
         graph_ms = time_loop(env, graph_step, steps)
         del graphs
 
+    # The same step as a training loop runs it: the frames are data, not parameters -- no gradient with respect to the
+    # source images (no scatter, no zero-fill, no unpack).  Reported beside `value`, which follows SURVEY.md section 8(d)
+    # (every gradient of row 11, grad_srcs included).
+    nosrc_ms = None
+    if not args.no_graph:
+        srcs_const = [b["srcs"].detach() for b in batches]
+        for b in batches:
+            for t in b["depth"] + [b["pose"]]:
+                t.grad = None
+        graphs = [coivo_b200.GraphedStep(b["depth"], b["pose"], b["K"], b["tgt"], sc) for b, sc in zip(batches, srcs_const)]
+        for i in range(max(warmup, 3)):
+            graphs[i % R].replay()
+        nosrc_ms = time_loop(env, lambda i: graphs[(warmup + i) % R].replay(), steps)
+        del graphs
+
     # end-to-end legs: pinned host buffers -> H2D -> fwd -> bwd -> D2H, through the C ABI.
     #   "device": the loss is read back, the gradients stay in HBM (a training step consumes them there)
     #   "host":   every gradient is copied back as well
@@ -405,8 +420,9 @@ def run_loss(args, cfg, cfg_id):
                "note": "dummy 28 M-parameter fp32 gradient all-reduce (NCCL), timed on its own"}
         del gbuf
 
-    ms_total, e2e_ms, kern_ms, graph_ms_max, e2e_full_ms, e2e_u8_ms = env.max_over_ranks(
-        [ms_total, e2e["device"]["ms"], kern_ms, graph_ms if graph_ms is not None else 0.0, e2e["host"]["ms"], e2e["u8"]["ms"]])
+    ms_total, e2e_ms, kern_ms, graph_ms_max, e2e_full_ms, e2e_u8_ms, nosrc_ms_max = env.max_over_ranks(
+        [ms_total, e2e["device"]["ms"], kern_ms, graph_ms if graph_ms is not None else 0.0, e2e["host"]["ms"], e2e["u8"]["ms"],
+         nosrc_ms if nosrc_ms is not None else 0.0])
     eager_ms = ms_total
     launch = "eager launches through the autograd.Function"
     if graph_ms is not None and graph_ms_max < ms_total:
@@ -448,6 +464,10 @@ def run_loss(args, cfg, cfg_id):
                        "launch": launch, "eager_ms_per_step": eager_ms / steps,
                        "graph_ms_per_step": (graph_ms_max / steps) if graph_ms is not None else None,
                        "eager_wall_ms_per_step": t_wall / steps * 1e3, "ddp_dummy_allreduce": ddp,
+                       "without_image_gradient": None if nosrc_ms is None else {
+                           "ms_per_step": nosrc_ms_max / steps, "frames_per_s": B_glob * steps / (nosrc_ms_max * 1e-3),
+                           "note": "the same step with srcs not requiring grad (what a training loop asks for): graph replay; "
+                                   "not the headline, which includes grad_srcs as SURVEY.md section 8(a) row 11 does"},
                        "cpu_affinity": f"{len(env.cpus)} CPUs of the GPU's NUMA node" if env.cpus else "unchanged"},
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_stale": stale, "peak_source": peak_src,

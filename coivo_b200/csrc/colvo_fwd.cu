@@ -439,27 +439,34 @@ __global__ void __launch_bounds__(kThreads)
       const double wg = (double)P.geo_weight / ((double)P.B * (double)P.N * (double)P.HW);
       for (int i = threadIdx.x; i < BNS * stat_chunks; i += kThreads) acc[1] += stat_part[(long long)i * kStatVals + 5] * wg;
     }
-    // smoothness: one warp per (b, k) sums the partials of that image's k_smooth CTAs (8 pairs per pass of the block,
-    // fixed order), then 1 / (mean d + eps) is applied (see k_smooth)
+    // smoothness: L lanes per (b, k) sum the partials of that image's k_smooth CTAs (kThreads / L pairs per pass of the
+    // block, fixed order), then 1 / (mean d + eps) is applied (see k_smooth).  L = the largest power of two <= 32 that
+    // still covers all B*S pairs in one pass when possible: 4 at config 2 (48 pairs, 80 CTAs each), 16 at config 4
+    // (16 pairs, 1 496 CTAs each) -- the loop is latency-bound, so more lanes per pair = fewer dependent loads each.
     {
-      for (int bk0 = 0; bk0 < P.B * P.S; bk0 += kThreads / 32) {
-        const int bk = bk0 + wid;
+      int L = 4;
+      while (L < 32 && (kThreads / (2 * L)) >= P.B * P.S) L *= 2;
+      const int grp = threadIdx.x / L, sub = threadIdx.x % L, per_pass = kThreads / L;
+      for (int bk0 = 0; bk0 < P.B * P.S; bk0 += per_pass) {
+        const int bk = bk0 + grp;
         const bool on = bk < P.B * P.S;
         const int b = on ? bk / P.S : 0, k = on ? bk - b * P.S : 0;
         const double* sp = smooth_part + ((long long)b * P.sm_blocks * P.S + k) * kSmVals;
         double sx = 0.0, sy = 0.0, sd = 0.0;
         if (on) {
-          for (int t = lane; t < P.sm_blocks; t += 32) {
+          for (int t = sub; t < P.sm_blocks; t += L) {
             const double* q = sp + (long long)t * P.S * kSmVals;
             sx += q[0];
             sy += q[1];
             sd += q[3];
           }
         }
-        sx = warp_sum(sx);
-        sy = warp_sum(sy);
-        sd = warp_sum(sd);
-        if (on && lane == 0) {
+        for (int o = 1; o < L; o <<= 1) {
+          sx += __shfl_xor_sync(0xffffffffu, sx, o);
+          sy += __shfl_xor_sync(0xffffffffu, sy, o);
+          sd += __shfl_xor_sync(0xffffffffu, sd, o);
+        }
+        if (on && sub == 0) {
           const double mean = sd / ((double)P.h[k] * (double)P.w[k]);
           acc[1] += (sx * wk_s[k][0] + sy * wk_s[k][1]) / (mean + (double)P.eps_disp);
         }

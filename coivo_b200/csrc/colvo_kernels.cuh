@@ -52,9 +52,11 @@ constexpr int kFwdTileH = kFwdWarps * kFwdRows;   // 12
 #define COLVO_STAT_PPT 8
 #endif
 constexpr int kStatPPT = COLVO_STAT_PPT;   // pixels per thread in the LCC statistics pass (one scale per CTA: the sweep)
-// training loss (S > 1): one CTA walks all scales of its pixel chunk (see k_warp_stats), 128 threads x 4 pixels per scale
+// COLVO_STATS_KINNER = 1 (training loss, S > 1): one CTA walks all scales of its pixel chunk (see k_warp_stats), 128 threads
+// x 4 pixels per scale.  Measured: the kernel alone 95.8 vs 97.1 us, the whole step 0.4407 vs 0.4342 ms (the smaller CTAs
+// overlap worse with the launches packed around them) -- off (profiles/r2_stats_kinner.log).
 #ifndef COLVO_STATS_KINNER
-#define COLVO_STATS_KINNER 1
+#define COLVO_STATS_KINNER 0
 #endif
 constexpr int kStatThreadsK = 128, kStatPPTK = 4;
 inline bool stats_k_inner(int S) { return COLVO_STATS_KINNER && S > 1; }
