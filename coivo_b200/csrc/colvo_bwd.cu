@@ -223,13 +223,13 @@ __global__ void __launch_bounds__(kBwdThreads, COLVO_MINB_BWD)
     float D_own;
     bool gvalid[NS];
     if constexpr (NS == 1) {
-      const float4 g4 = __ldg(geo_in + (long long)(b * P.S + k) * P.HW + qo);
+      const float4 g4 = ld_stream(geo_in + (long long)(b * P.S + k) * P.HW + qo);
       gu = V(g4.x); gv = V(g4.y); giz = V(g4.z);
       D_own = g4.w;
       gvalid[0] = (__float_as_uint(g4.w) & 1u) != 0u;
     } else {
-      const float4 ga4 = __ldg(geo_in + (long long)(b * P.S + k) * P.HW + qo);
-      const float4 gb4 = __ldg(geo_in + (long long)((P.B + b) * P.S + k) * P.HW + qo);
+      const float4 ga4 = ld_stream(geo_in + (long long)(b * P.S + k) * P.HW + qo);
+      const float4 gb4 = ld_stream(geo_in + (long long)((P.B + b) * P.S + k) * P.HW + qo);
       gu = V(ga4.x, ga4.y); gv = V(ga4.z, ga4.w); giz = V(gb4.x, gb4.y);
       D_own = gb4.z;
       const unsigned vb = __float_as_uint(gb4.w);

@@ -295,6 +295,29 @@ __device__ __forceinline__ float4 ldg_f4_hint(const float4* p, unsigned long lon
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
   return v;
 }
+// 16-byte load of data that is read exactly once by this grid: no L1 allocation, so that it does not displace the source
+// texels the kernel keeps gathering (COLVO_STREAM_LOADS = 0: a plain read-only load)
+#ifndef COLVO_STREAM_LOADS
+#define COLVO_STREAM_LOADS 1
+#endif
+__device__ __forceinline__ float4 ld_stream(const float4* p) {
+#if COLVO_STREAM_LOADS
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+#else
+  return __ldg(p);
+#endif
+}
+__device__ __forceinline__ float ld_stream(const float* p) {
+#if COLVO_STREAM_LOADS
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];\n" : "=f"(v) : "l"(p));
+  return v;
+#else
+  return __ldg(p);
+#endif
+}
 // the same with the 32-bit shared-window address already at hand (hoisted out of an unrolled staging loop)
 __device__ __forceinline__ void cp_async16_s(unsigned saddr, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(gmem));
