@@ -203,14 +203,20 @@ __global__ void __launch_bounds__(kThreads)
 // scales gather from the same source lines, so scales 1.. find them in L1 (with one CTA per (b, k) they sat in the L1s of
 // different SMs); 128-thread CTAs of kStatPPTK pixels per thread and scale keep the CTA count (and the pixels in flight per
 // thread) of the one-scale form.  !KIN (consistency sweep, S = 1): blockIdx.y = (b, k), 256 threads, kStatPPT pixels each.
-template <bool KIN> struct StatCfg { static constexpr int NT = KIN ? kStatThreadsK : kThreads, PPT = KIN ? kStatPPTK : kStatPPT; };
-template <int NS, bool GEO, bool PK, bool KIN>
-__global__ void __launch_bounds__(StatCfg<KIN>::NT, COLVO_MINB_STATS * kThreads / StatCfg<KIN>::NT)
+// MODE 0: one scale per CTA, kStatPPT pixels per thread (sweep); 1: all scales per CTA (KIN); 2: one scale per CTA,
+// kStatPPTTrain pixels per thread (training loss)
+template <int MODE> struct StatCfg {
+  static constexpr bool KIN = MODE == 1;
+  static constexpr int NT = KIN ? kStatThreadsK : kThreads, PPT = KIN ? kStatPPTK : (MODE == 2 ? kStatPPTTrain : kStatPPT);
+};
+template <int NS, bool GEO, bool PK, int MODE>
+__global__ void __launch_bounds__(StatCfg<MODE>::NT, COLVO_MINB_STATS * kThreads / StatCfg<MODE>::NT)
     k_warp_stats(KP P, double* __restrict__ part, uint8_t* __restrict__ valid_out, float4* __restrict__ iw_out,
                  float4* __restrict__ geo_out, float* __restrict__ occ_out) {
   constexpr int NA = GEO ? kStatVals : 5;      // accumulators per source (the 6th only with the geometric term)
   constexpr int NV = NA * NS;
-  constexpr int NT = StatCfg<KIN>::NT, PPT = StatCfg<KIN>::PPT;
+  constexpr bool KIN = StatCfg<MODE>::KIN;
+  constexpr int NT = StatCfg<MODE>::NT, PPT = StatCfg<MODE>::PPT;
   typedef Vn<NS> V;
   __shared__ double sm[(NT / 32) * NV];
   pdl_trigger();                               // k_lcc_solve / k_photo_fwd may start their prologues in this kernel's tail
@@ -655,7 +661,9 @@ cudaError_t launch_forward(const KP& P, const FwdBuffers& Wk, float* loss, float
     auto pick = [&](auto ns, auto geoc, auto pkc) {
       constexpr int NSc = decltype(ns)::value;
       constexpr bool Gc = decltype(geoc)::value, PKc = decltype(pkc)::value;
-      if (kin) run(k_warp_stats<NSc, Gc, PKc, true>); else run(k_warp_stats<NSc, Gc, PKc, false>);
+      if (kin) run(k_warp_stats<NSc, Gc, PKc, 1>);
+      else if (P.S > 1) run(k_warp_stats<NSc, Gc, PKc, 2>);
+      else run(k_warp_stats<NSc, Gc, PKc, 0>);
     };
     using I1 = std::integral_constant<int, 1>; using I2 = std::integral_constant<int, 2>;
     using T = std::true_type; using F = std::false_type;
@@ -735,7 +743,7 @@ cudaError_t launch_consistency(const KP& P0, double* stat_part, int stat_chunks,
     float* abp = ab + 2 * p0;
     {
       ScopedKernelTimer tm(3, st);
-      k_warp_stats<1, false, false, false><<<dim3(stat_chunks, P.B), kThreads, 0, st>>>(P, sp, nullptr, iw, nullptr, nullptr);
+      k_warp_stats<1, false, false, 0><<<dim3(stat_chunks, P.B), kThreads, 0, st>>>(P, sp, nullptr, iw, nullptr, nullptr);
     }
     k_lcc_solve<<<P.B, 32, 0, st>>>(P, sp, stat_chunks, abp, nullptr);
     {

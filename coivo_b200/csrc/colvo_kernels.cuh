@@ -59,8 +59,16 @@ constexpr int kStatPPT = COLVO_STAT_PPT;   // pixels per thread in the LCC stati
 #define COLVO_STATS_KINNER 0
 #endif
 constexpr int kStatThreadsK = 128, kStatPPTK = 4;
+// one-scale-per-CTA form: 4 pixels per thread for the training loss (S > 1: -0.6 % per step against 8), kStatPPT = 8 for the
+// single-scale consistency sweep (4 is 3 % slower there) -- profiles/r2_step_level_ab.log
+#ifndef COLVO_STAT_PPT_TRAIN
+#define COLVO_STAT_PPT_TRAIN 4
+#endif
+constexpr int kStatPPTTrain = COLVO_STAT_PPT_TRAIN;
 inline bool stats_k_inner(int S) { return COLVO_STATS_KINNER && S > 1; }
-inline int stats_pixels_per_cta(int S) { return stats_k_inner(S) ? kStatThreadsK * kStatPPTK : kThreads * kStatPPT; }
+inline int stats_pixels_per_cta(int S) {
+  return stats_k_inner(S) ? kStatThreadsK * kStatPPTK : kThreads * (S > 1 ? kStatPPTTrain : kStatPPT);
+}
 constexpr int kStatVals = 6;     // per (frame, chunk): n, Sx, Sy, Sxx, Sxy, sum of geometric-consistency diffs
 #ifndef COLVO_SM_BW
 #define COLVO_SM_BW 64
