@@ -372,7 +372,7 @@ def run_loss(args, cfg, cfg_id):
     # The same step as a training loop runs it: the frames are data, not parameters -- no gradient with respect to the
     # source images (no scatter, no zero-fill, no unpack).  Reported beside `value`, which follows SURVEY.md section 8(d)
     # (every gradient of row 11, grad_srcs included).
-    nosrc_ms = None
+    nosrc_ms = merged_ms = None
     if not args.no_graph:
         srcs_const = [b["srcs"].detach() for b in batches]
         for b in batches:
@@ -382,6 +382,15 @@ def run_loss(args, cfg, cfg_id):
         for i in range(max(warmup, 3)):
             graphs[i % R].replay()
         nosrc_ms = time_loop(env, lambda i: graphs[(warmup + i) % R].replay(), steps)
+        del graphs
+        # ... and with the warp-aggregated scatter (COLVO_F_SCATTER_MERGE), the form north_star names; it is the slower one
+        for b in batches:
+            for t in b["depth"] + [b["pose"], b["srcs"]]:
+                t.grad = None
+        graphs = [coivo_b200.GraphedStep(b["depth"], b["pose"], b["K"], b["tgt"], b["srcs"], scatter="merged") for b in batches]
+        for i in range(max(warmup, 3)):
+            graphs[i % R].replay()
+        merged_ms = time_loop(env, lambda i: graphs[(warmup + i) % R].replay(), steps)
         del graphs
 
     # end-to-end legs: pinned host buffers -> H2D -> fwd -> bwd -> D2H, through the C ABI.
@@ -420,9 +429,9 @@ def run_loss(args, cfg, cfg_id):
                "note": "dummy 28 M-parameter fp32 gradient all-reduce (NCCL), timed on its own"}
         del gbuf
 
-    ms_total, e2e_ms, kern_ms, graph_ms_max, e2e_full_ms, e2e_u8_ms, nosrc_ms_max = env.max_over_ranks(
+    ms_total, e2e_ms, kern_ms, graph_ms_max, e2e_full_ms, e2e_u8_ms, nosrc_ms_max, merged_ms_max = env.max_over_ranks(
         [ms_total, e2e["device"]["ms"], kern_ms, graph_ms if graph_ms is not None else 0.0, e2e["host"]["ms"], e2e["u8"]["ms"],
-         nosrc_ms if nosrc_ms is not None else 0.0])
+         nosrc_ms if nosrc_ms is not None else 0.0, merged_ms if merged_ms is not None else 0.0])
     eager_ms = ms_total
     launch = "eager launches through the autograd.Function"
     if graph_ms is not None and graph_ms_max < ms_total:
@@ -468,6 +477,10 @@ def run_loss(args, cfg, cfg_id):
                            "ms_per_step": nosrc_ms_max / steps, "frames_per_s": B_glob * steps / (nosrc_ms_max * 1e-3),
                            "note": "the same step with srcs not requiring grad (what a training loop asks for): graph replay; "
                                    "not the headline, which includes grad_srcs as SURVEY.md section 8(a) row 11 does"},
+                       "warp_aggregated_scatter": None if merged_ms is None else {
+                           "ms_per_step": merged_ms_max / steps,
+                           "note": "the headline step with scatter='merged' (COLVO_F_SCATTER_MERGE: coincident taps summed in the warp, "
+                                   "half the global reductions); graph replay.  Slower than the default vector-RED scatter, hence opt-in"},
                        "cpu_affinity": f"{len(env.cpus)} CPUs of the GPU's NUMA node" if env.cpus else "unchanged"},
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_stale": stale, "peak_source": peak_src,

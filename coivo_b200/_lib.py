@@ -26,6 +26,7 @@ F_SAVE_FOR_BWD = 4
 F_NO_SRC_GRAD = 8
 F_PACKED_BF16 = 16
 F_HOST_U8 = 32
+F_SCATTER_MERGE = 64
 
 MAX_SCALES = 4
 MAX_SOURCES = 2

@@ -16,6 +16,8 @@
 //   k_pose_final     the same epilogue blocks on their own when S = 1
 #include <string.h>
 
+#include <type_traits>
+
 #include "colvo_kernels.cuh"
 
 // Ablation builds for the timing experiments logged under profiles/ (scripts/build_variants.py): they skip the
@@ -41,10 +43,8 @@
 // pixel, source and scale instead of four (L2 atomic sectors 68 -> 36 per warp).  Built, parity-green
 // (profiles/r2_scatter_merge.log) and measured SLOWER on B200: 225 us against 199 us for the plain vector-RED scatter
 // (211 vs 203 us at 96 registers): the exchange costs more issue slots and shared-memory bandwidth -- which this kernel
-// is short of -- than the L2 sectors it saves.  Hence a build knob, off by default.
-#ifndef COLVO_BWD_SCATTER_MERGE
-#define COLVO_BWD_SCATTER_MERGE 0
-#endif
+// is short of -- than the L2 sectors it saves.  Both forms ship: the descriptor flag COLVO_F_SCATTER_MERGE selects the
+// aggregated one at run time (template parameter MERGE), the default is the plain vector-RED scatter.
 #ifndef COLVO_BWD_TMA       // 1: the coefficient tile of a scale (34 x 6 windows x 3 channels of 16-byte texels) is ONE TMA
 #define COLVO_BWD_TMA 1     //    box load issued by one thread (UTMALDG; zero fill outside the image by the hardware);
 #endif                      //    0: 16-byte cp.async (LDGSTS) by every thread
@@ -92,7 +92,7 @@ struct BwdConstV {         // per scale, lane n = warped frame (n, k); built onc
   Vn<NS> wl1;              // weight of the L1 term's sign at the own pixel: wscale * (1 - alpha) / 3 * a
 };
 
-template <int NS, bool GEO, bool PK>
+template <int NS, bool GEO, bool PK, bool MERGE>
 __global__ void __launch_bounds__(kBwdThreads, COLVO_MINB_BWD)
     k_photo_bwd(KP P, const float* __restrict__ grad_loss, const uint8_t* __restrict__ sel,
                 const double* __restrict__ saved_frame, const double* __restrict__ saved_scale,
@@ -204,6 +204,10 @@ __global__ void __launch_bounds__(kBwdThreads, COLVO_MINB_BWD)
     mbar_arrive_cp_async(&mbar[k & 1]);      // this thread's share of full[k & 1]
 #endif
   };
+  // warp-aggregated scatter: the active lanes of a warp are a prefix (one tile row: px grows with the lane); lane 0 has no
+  // left neighbour: its exchange slot keeps a sentinel offset that matches no texel
+  const unsigned amask = MERGE ? __ballot_sync(0xffffffffu, in_img) : 0u;
+  if (MERGE && tx == 0) xch[0][0] = xch[0][1] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
   if (tid == 0) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) mbar_init(&mbar[i], (COLVO_BWD_TMA && i < 2) ? 1 : kBwdThreads);   // full[0..1], empty[0..1]
@@ -381,7 +385,7 @@ __global__ void __launch_bounds__(kBwdThreads, COLVO_MINB_BWD)
             const float h0 = hq[0].lane(i), h1 = hq[1].lane(i), h2 = hq[2].lane(i);
             const int o00 = r0[i] + t[i].x0, o01 = r0[i] + t[i].x1, o10 = r1[i] + t[i].x0, o11 = r1[i] + t[i].x1;
             CV_CHECK(o00 >= 0 && o11 < P.HW && o01 < P.HW && o10 < P.HW);
-#if COLVO_BWD_SCATTER_MERGE
+            if constexpr (MERGE) {
             // Warp-aggregated scatter (north_star: no contended global atomics).  Neighbouring pixels of a row sample
             // neighbouring texels, so the right-hand taps (x1, y0), (x1, y1) of lane l usually ARE the left-hand taps
             // (x0, y0), (x0, y1) of lane l + 1.  Every lane parks its x1 taps -- three channel values and the texel
@@ -404,12 +408,12 @@ __global__ void __launch_bounds__(kBwdThreads, COLVO_MINB_BWD)
               if (!m && f >= 0) red_add3(gs + (unsigned)f, d.x, d.y, d.z);          // the neighbour's tap lies elsewhere
               if (!has_right) red_add3(gs + (unsigned)ox1, ax1 * h0, ax1 * h1, ax1 * h2);   // right-most pixel of the row segment
             }
-#else
+            } else {
             red_add3(gs + (unsigned)o00, a00 * h0, a00 * h1, a00 * h2);
             red_add3(gs + (unsigned)o01, a01 * h0, a01 * h1, a01 * h2);
             red_add3(gs + (unsigned)o10, a10 * h0, a10 * h1, a10 * h2);
             red_add3(gs + (unsigned)o11, a11 * h0, a11 * h1, a11 * h2);
-#endif
+            }
           }
         }
         // geometric consistency (f-2): gradient to Z' directly, to the sampled source depth (scatter) and,
@@ -671,10 +675,10 @@ __global__ void __launch_bounds__(kThreads) k_zero(float4* __restrict__ a, long 
 }
 
 template <int NS>
-static size_t photo_bwd_smem() {
+static size_t photo_bwd_smem(bool merge) {
   return sizeof(float4) * 2 * kCoefBuf + sizeof(double) * (kBwdThreads / 32) * NS * 12 +
          1024 /* per-frame constants, poses */ + 64 /* mbarriers */ +
-         (COLVO_BWD_SCATTER_MERGE ? sizeof(float4) * 2 * kBwdThreads : 0) /* scatter exchange slots */;
+         (merge ? sizeof(float4) * 2 * kBwdThreads : 0) /* scatter exchange slots */;
 }
 
 cudaError_t launch_backward(const KP& P, const BwdBuffers& Wk, const float* grad_loss, const uint8_t* sel,
@@ -719,13 +723,18 @@ cudaError_t launch_backward(const KP& P, const BwdBuffers& Wk, const float* grad
       if (e == cudaSuccess) e = cudaGetLastError();
     };
     const bool geo = P.src_depth != nullptr, pk = (P.flags & 16u) != 0;
-    if (P.N == 1) {
-      if (geo) { if (pk) launch(k_photo_bwd<1, true, true>, photo_bwd_smem<1>()); else launch(k_photo_bwd<1, true, false>, photo_bwd_smem<1>()); }
-      else { if (pk) launch(k_photo_bwd<1, false, true>, photo_bwd_smem<1>()); else launch(k_photo_bwd<1, false, false>, photo_bwd_smem<1>()); }
-    } else {
-      if (geo) { if (pk) launch(k_photo_bwd<2, true, true>, photo_bwd_smem<2>()); else launch(k_photo_bwd<2, true, false>, photo_bwd_smem<2>()); }
-      else { if (pk) launch(k_photo_bwd<2, false, true>, photo_bwd_smem<2>()); else launch(k_photo_bwd<2, false, false>, photo_bwd_smem<2>()); }
-    }
+    // MERGE exists for planar sources only (packed bf16 images carry no source gradient, hence no scatter)
+    const bool merge = (P.flags & 64u) != 0 && grad_srcs != nullptr && !pk;
+    auto pick = [&](auto ns, auto geoc) {
+      constexpr int NSc = decltype(ns)::value;
+      constexpr bool Gc = decltype(geoc)::value;
+      if (pk) launch(k_photo_bwd<NSc, Gc, true, false>, photo_bwd_smem<NSc>(false));
+      else if (merge) launch(k_photo_bwd<NSc, Gc, false, true>, photo_bwd_smem<NSc>(true));
+      else launch(k_photo_bwd<NSc, Gc, false, false>, photo_bwd_smem<NSc>(false));
+    };
+    using I1 = std::integral_constant<int, 1>; using I2 = std::integral_constant<int, 2>;
+    if (P.N == 1) { if (geo) pick(I1{}, std::true_type{}); else pick(I1{}, std::false_type{}); }
+    else { if (geo) pick(I2{}, std::true_type{}); else pick(I2{}, std::false_type{}); }
   }
   if (e != cudaSuccess) return e;
   // epilogue: pose reduction, source-gradient unpack and the up-sample adjoint are independent of each other, so they

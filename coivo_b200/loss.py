@@ -126,6 +126,8 @@ def _plan(B, N, S, H, W, flags, alpha, smooth_weight, geo_weight):
 class _PhotoLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pose, K, tgt, srcs, alpha, smooth_weight, lcc, lcc_detach, want_valid, src_depth, geo_weight, *depth):
+        merge = bool(want_valid & 16)         # bit 4: warp-aggregated scatter in the backward (COLVO_F_SCATTER_MERGE)
+        want_valid &= 15
         want_occ = want_valid == 2            # 2: masks and the soft occlusion mask of the geometric term
         want_valid = bool(want_valid)
         B, N, S, H, W, packed = _check_inputs(depth, pose, K, tgt, srcs)
@@ -150,6 +152,8 @@ class _PhotoLossFn(torch.autograd.Function):
         flags = (_lib.F_LCC if lcc else 0) | (_lib.F_LCC_DETACH if lcc_detach else 0) | (_lib.F_PACKED_BF16 if packed else 0)
         if needs_grad:
             flags |= _lib.F_SAVE_FOR_BWD
+        if merge:
+            flags |= _lib.F_SCATTER_MERGE
         desc, nbytes, nsaved = _plan(B, N, S, H, W, flags, alpha, smooth_weight, geo_weight)
         with torch.cuda.device(dev):
             ws = _Workspace.get(nbytes, dev)
@@ -235,6 +239,7 @@ def photometric_loss(
     src_depth: Optional[torch.Tensor] = None,
     geo_weight: float = 0.0,
     return_occlusion: bool = False,
+    scatter: str = "atomic",
 ):
     """View-synthesis photometric loss with LCC, min-reprojection / auto-mask and edge-aware
     smoothness over S scales and N neighbouring frames.
@@ -251,9 +256,16 @@ def photometric_loss(
     Returns the 0-dim loss, or `(loss, valid u8 [B,N,S,H,W], sel u8 [B,S,H,W], ab [B,N,S,2])`; with
     `return_occlusion=True` (needs the geometric term) a fifth item `occ [B,N,S,H,W]`: SC-Depth's soft occlusion mask
     `1 - diff` (0 where the projection is invalid), a constant by-product of that term.
+
+    `scatter="merged"` makes the backward sum coincident bilinear taps of neighbouring pixels inside the warp before they go
+    to `grad_srcs` (half the global reductions, no contended atomics; same results, measured slower on B200 than the
+    default `"atomic"` vector-RED scatter -- DESIGN.md section 4).
     """
+    if scatter not in ("atomic", "merged"):
+        raise ValueError("scatter must be 'atomic' or 'merged'")
+    mode = (2 if return_occlusion else int(bool(return_masks))) | (16 if scatter == "merged" else 0)
     out = _PhotoLossFn.apply(pose, K, tgt, srcs, float(alpha), float(smooth_weight), bool(lcc), bool(lcc_detach),
-                             2 if return_occlusion else int(bool(return_masks)), src_depth, float(geo_weight), *depth)
+                             mode, src_depth, float(geo_weight), *depth)
     if return_occlusion:
         loss, ab, sel, valid, occ = out
         return loss, valid, sel, ab, occ

@@ -46,6 +46,11 @@ extern "C" {
 #define COLVO_F_HOST_U8 32u        /* colvo_photo_step_host only: h_tgt / h_srcs are uint8 frames (what a video loader holds);
                                       they are copied as bytes and widened on the device, x = u8 * (1.0f / 255.0f)   */
 
+#define COLVO_F_SCATTER_MERGE 64u   /* backward: warp-aggregated scatter into grad_srcs -- coincident bilinear taps of neighbouring
+                                      pixels are summed inside the warp (shared-memory exchange, no shared atomics) before they go
+                                      to global memory: two vector REDs per pixel, source and scale instead of four.  Same results;
+                                      measured slower than the default scatter on B200, hence opt-in */
+
 /* negative error codes */
 #define COLVO_E_BAD_DESC (-1)
 #define COLVO_E_WORKSPACE (-2)

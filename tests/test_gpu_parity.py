@@ -67,10 +67,10 @@ def adjudicate(d, sel, s0, ab, name, **kw):
     return stats
 
 
-def check_against_oracle(d, depth_atol=0.0, name=None, **kw):
+def check_against_oracle(d, depth_atol=0.0, name=None, scatter=None, **kw):
     N, S = d["srcs"].shape[1], len(d["depth"])
     name = name or f"B{d['tgt'].shape[0]}_{d['tgt'].shape[2]}x{d['tgt'].shape[3]}_N{N}_S{S}" + "".join(f"_{k}={v}" for k, v in kw.items())
-    loss, valid, sel, ab, gd, gT, gs = run_cuda(d, **kw)
+    loss, valid, sel, ab, gd, gT, gs = run_cuda(d, **(dict(kw, scatter=scatter) if scatter else kw))
     with torch.no_grad():
         l0, v0, s0, ab0 = O.photometric_loss(d["depth"], d["pose"], d["K"], d["tgt"], d["srcs"], return_masks=True, **kw)
     assert torch.equal(valid, v0), "valid mask must be bit-exact"
@@ -110,6 +110,13 @@ def test_parity_small(B, H, W, N, S):
                                 dict(smooth_weight=0.0)])
 def test_parity_flags(kw):
     check_against_oracle(make_triplets(2, 48, 64, seed=21), **kw)
+
+
+@pytest.mark.parametrize("B,H,W,N,S", [(2, 64, 96, 2, 4), (1, 37, 53, 1, 3), (2, 256, 320, 2, 4)])
+def test_parity_warp_aggregated_scatter(B, H, W, N, S):
+    """COLVO_F_SCATTER_MERGE (north_star: a scatter-add that avoids contended global atomics by warp aggregation): the same
+    parity protocol with `scatter="merged"`; ragged sizes exercise warps whose active lanes are a strict prefix."""
+    check_against_oracle(make_triplets(B, H, W, N=N, S=S, seed=71 + H), name=f"merged_scatter_B{B}_{H}x{W}_N{N}_S{S}", scatter="merged")
 
 
 def test_parity_config2_one_triplet_full_size():
