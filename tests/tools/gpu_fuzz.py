@@ -59,7 +59,11 @@ for case in range(n_cases):
             kw = dict(kw, src_depth=sdg, geo_weight=0.5)
             osd = sd.clone().requires_grad_()
             okw = dict(okw, src_depth=osd, geo_weight=0.5)
-        loss, valid, sel, ab = coivo_b200.photometric_loss(depth, pose, d["K"].to(DEV), d["tgt"].to(DEV), srcs, return_masks=True, **kw)
+        merged = (case % 3 == 1)      # every third planar case runs the warp-aggregated scatter (COLVO_F_SCATTER_MERGE)
+        if merged:
+            kw_tag = dict(kw_tag, scatter="merged")
+        loss, valid, sel, ab = coivo_b200.photometric_loss(depth, pose, d["K"].to(DEV), d["tgt"].to(DEV), srcs, return_masks=True,
+                                                           scatter="merged" if merged else "atomic", **kw)
     loss.backward(); torch.cuda.synchronize()
     kw = {k: v for k, v in okw.items() if k not in ("src_depth", "geo_weight")}
     with torch.no_grad():
