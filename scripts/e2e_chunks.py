@@ -7,9 +7,12 @@ dev = torch.device("cuda:0")
 d = make_triplets(12, 256, 320, seed=0)
 pin = lambda t: t.pin_memory()
 h = ([pin(x) for x in d["depth"]], pin(d["pose"]), pin(d["K"]), pin(d["tgt"]), pin(d["srcs"]))
-for mode in ("device", "host"):
+to_u8 = lambda t: (t * 255.0).round().clamp_(0, 255).to(torch.uint8)
+h8 = (h[0], h[1], h[2], pin(to_u8(d["tgt"])), pin(to_u8(d["srcs"])))
+for mode, images in (("device", "f32"), ("host", "f32"), ("device", "u8")):
+    h = h8 if images == "u8" else h
     for chunks in (1, 2, 3, 4, 6, 12):
-        st = coivo_b200.HostStepper(12, 2, 4, 256, 320, device=dev, chunks=chunks, grads=mode)
+        st = coivo_b200.HostStepper(12, 2, 4, 256, 320, device=dev, chunks=chunks, grads=mode, images=images)
         for _ in range(5):
             st.step(*h)
         st.finish()
@@ -19,5 +22,5 @@ for mode in ("device", "host"):
             st.step(*h)
         st.join(); e1.record(); st.finish()
         ms = e0.elapsed_time(e1) / 200
-        print(f"grads={mode} chunks={chunks}: {ms:.3f} ms/step = {12 / ms * 1e3:.0f} triplets/s", flush=True)
+        print(f"grads={mode} images={images} chunks={chunks}: {ms:.3f} ms/step = {12 / ms * 1e3:.0f} triplets/s", flush=True)
         del st
